@@ -1,0 +1,352 @@
+#!/usr/bin/env python
+"""Benchmark of the lineax solve hot path on B200 (contract: see the task statement).
+
+A "step" is one pass of the hot path over one batch of synthetic systems.
+Default workload = BASELINE.json configs[1]: vmapped LU on 65536 independent 32x32 fp32
+systems (`--workload lu32`); `--workload cg256` is configs[2] (4096 x 256^2 SPD fp32 CG).
+Multi-GPU (`--gpus N`, launched under torchrun): batch-sharded, no data-path collective,
+every rank solves its own full-size batch (weak scaling).
+
+`--impl reference` times the CPU implementation of the same path (the oracle port: JAX is
+not installable in this image) on the host cores.
+"""
+import argparse
+import ctypes
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+WORKLOADS = {
+    "lu32": dict(batch=65536, n=32, desc="vmapped lx.LU on 65536 independent 32x32 fp32 systems"),
+    "cg256": dict(batch=4096, n=256, desc="vmapped lx.CG on 4096 independent 256x256 SPD fp32 systems, rtol=atol=1e-6"),
+}
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs, burst copy)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    FIELDS = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+              "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.idx = gpu_index
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.p = None
+
+    def start(self):
+        try:
+            self.p = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits",
+                 "-i", str(self.idx), "-lms", "100"], stdout=self.f, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.p = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        if self.p is None:
+            return out
+        time.sleep(0.15)
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except Exception:
+            self.p.kill()
+        self.f.flush()
+        rows = [r.split(",") for r in open(self.f.name).read().strip().splitlines() if r.strip()]
+        os.unlink(self.f.name)
+        sm, mx, reasons = [], [], set()
+        for r in rows:
+            try:
+                sm.append(float(r[1])), mx.append(float(r[2]))
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
+                    if "Active" in v and "Not" not in v:
+                        reasons.add(name)
+            except Exception:
+                pass
+        if sm:
+            out = {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons),
+                   "samples": len(sm)}
+        return out
+
+
+def make_inputs(workload, seed):
+    from oracle import gen
+
+    w = WORKLOADS[workload]
+    if workload == "lu32":
+        rng = np.random.default_rng(seed)
+        a = rng.standard_normal((w["batch"], w["n"], w["n"]), dtype=np.float32)
+        x = rng.standard_normal((w["batch"], w["n"]), dtype=np.float32)
+        b = np.einsum("bij,bj->bi", a, x)
+        return a, b
+    # cg256: the reference's own easy generator (benchmarks/solver_speeds.py:146-152), 256 distinct
+    # matrices tiled 16x (generation of 4096 matrices on the host would dominate the run time)
+    a, b, _ = gen.easy_problem(seed, w["n"], np.float32, spd=True, batch=256)
+    reps = w["batch"] // 256
+    return np.tile(a, (reps, 1, 1)), np.tile(b, (reps, 1))
+
+
+def cpu_port_step(workload, a, b, threads=None):
+    """One pass of the oracle (CPU restatement) over a sample; returns systems solved."""
+    from oracle import clib
+    import oracle
+
+    if workload == "lu32":
+        clib.lu_factor_solve(a, b, threads)
+        return a.shape[0]
+    for i in range(a.shape[0]):
+        oracle.cg(a[i], b[i], 1e-6, 1e-6)
+    return a.shape[0]
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle import clib
+
+    clib.lib()
+    w = WORKLOADS[args.workload]
+    cores = os.cpu_count() or 1
+    sample = w["batch"] if args.workload == "lu32" else 256
+    a, b = make_inputs(args.workload, 0)
+    a, b = a[:sample], b[:sample]
+    for _ in range(args.warmup):
+        cpu_port_step(args.workload, a, b)
+    t0 = time.perf_counter()
+    done = 0
+    for _ in range(args.steps):
+        done += cpu_port_step(args.workload, a, b)
+    dt = time.perf_counter() - t0
+    value = done / dt
+    line = {
+        "impl": "reference", "metric": f"batched solves/sec ({w['desc']})", "value": value,
+        "unit": "solves/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": args.workload, "batch_per_step": sample, "n": w["n"]},
+        "cpu_baseline": {"value": value, "unit": "solves/s", "cores": cores if args.workload == "lu32" else 1,
+                         "kind": "port",
+                         "sample": f"{sample} systems per step; oracle port (C getf2 for LU on a thread pool / "
+                                   "NumPy CG), JAX unavailable so lineax itself cannot run"},
+        "e2e": {"value": value, "unit": "solves/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="native", choices=["native", "reference"])
+    ap.add_argument("--workload", default="lu32", choices=sorted(WORKLOADS))
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "native" else args.warmup
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch
+    import torch.distributed as dist
+
+    import lineax_b200 as lx
+    from lineax_b200 import _native as nat
+    from lineax_b200 import _ops
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    w = WORKLOADS[args.workload]
+    batch, n = w["batch"], w["n"]
+    a_h, b_h = make_inputs(args.workload, rank)  # each rank: its own batch (weak scaling)
+    A = torch.as_tensor(a_h).cuda()
+    B = torch.as_tensor(b_h).cuda()
+    stream = torch.cuda.current_stream().cuda_stream
+
+    if args.workload == "lu32":
+        X = torch.empty_like(B)
+        fn = nat.fn("lxb_lu_factor_solve_f32")
+        argv = (A.data_ptr(), n * n, B.data_ptr(), n, X.data_ptr(), None, None, batch, n, stream)
+
+        def step():
+            nat.check(fn(*argv), "lxb_lu_factor_solve_f32")
+
+        alg_bytes = batch * (n * n + 2 * n) * 4  # 4352 B per solve, fused, state not written
+        kernel_name = "lu_warp_kernel<float,32,true>"
+    else:
+        X = torch.empty_like(B)
+        RES = torch.empty(batch, dtype=torch.int32, device="cuda")
+        STEPS = torch.empty(batch, dtype=torch.int32, device="cuda")
+        fn = nat.fn("lxb_cg_f32")
+        argv = (A.data_ptr(), n * n, B.data_ptr(), n, None, 0, X.data_ptr(), RES.data_ptr(), STEPS.data_ptr(),
+                batch, n, 1e-6, 1e-6, 10 * n, 10, 0, None, 0, stream)
+
+        def step():
+            nat.check(fn(*argv), "lxb_cg_f32")
+
+        alg_bytes = None  # depends on the iteration counts, filled in after the run
+        kernel_name = "cg_cta_kernel<float>"
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        step()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    launches0 = nat.launch_count()
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
+    barrier()
+    ev[0].record()
+    for i in range(args.steps):
+        step()
+        ev[i + 1].record()
+    barrier()
+    launches = nat.launch_count() - launches0
+    clocks = sampler.stop() if rank == 0 else None
+    total_ms = ev[0].elapsed_time(ev[-1])
+    per_launch_ms = [ev[i].elapsed_time(ev[i + 1]) for i in range(args.steps)]
+    t = torch.tensor([total_ms], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    total_ms_max = float(t.item())
+    value = world * batch * args.steps / (total_ms_max * 1e-3)
+
+    if args.workload == "cg256":
+        k = STEPS.cpu().numpy().astype(np.int64)
+        n_mv = 1 + k + k // 10  # operator applications of the reference algorithm
+        alg_bytes = int(n_mv.sum()) * n * n * 4
+
+    # ---- e2e: host buffers through the C ABI, H2D + D2H inside the timed region ----
+    e2e = None
+    if args.workload == "lu32":
+        a_pin = torch.as_tensor(a_h).pin_memory()
+        b_pin = torch.as_tensor(b_h).pin_memory()
+        x_pin = torch.empty(batch, n, dtype=torch.float32).pin_memory()
+        nbytes = nat.fn("lxb_host_scratch_bytes")(batch, n, 4)
+        scratch = torch.empty(nbytes, dtype=torch.uint8, device="cuda")
+        hfn = nat.fn("lxb_lu_factor_solve_f32_host")
+
+        def e2e_step():
+            nat.check(hfn(a_pin.data_ptr(), b_pin.data_ptr(), x_pin.data_ptr(), batch, n,
+                          scratch.data_ptr(), nbytes, stream), "lxb_lu_factor_solve_f32_host")
+
+        for _ in range(2):
+            e2e_step()
+        barrier()
+        t0 = time.perf_counter()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        e2e_steps = max(3, min(args.steps, 10))
+        for _ in range(e2e_steps):
+            e2e_step()
+        e1.record()
+        barrier()
+        ms = e0.elapsed_time(e1)
+        t2 = torch.tensor([ms], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(t2, op=dist.ReduceOp.MAX)
+        e2e = {"value": world * batch * e2e_steps / (float(t2.item()) * 1e-3), "unit": "solves/s",
+               "h2d_bytes_per_step": int(a_h.nbytes + b_h.nbytes), "d2h_bytes_per_step": int(batch * n * 4),
+               "steps": e2e_steps, "api": "lxb_lu_factor_solve_f32_host (pinned host buffers)"}
+        x_check = x_pin.numpy().copy()
+    else:
+        a_pin = torch.as_tensor(a_h).pin_memory()
+        b_pin = torch.as_tensor(b_h).pin_memory()
+        cg = lx.CG(rtol=1e-6, atol=1e-6)
+        solve = torch.func.vmap(lambda m, v: lx.linear_solve(
+            lx.MatrixLinearOperator(m, lx.positive_semidefinite_tag), v, cg, throw=False).value)
+
+        def e2e_step():
+            return solve(a_pin.cuda(non_blocking=True), b_pin.cuda(non_blocking=True)).cpu()
+
+        e2e_step()
+        barrier()
+        e2e_steps = 3
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            x_check = e2e_step().numpy()
+        barrier()
+        dt = time.perf_counter() - t0
+        t2 = torch.tensor([dt], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(t2, op=dist.ReduceOp.MAX)
+        e2e = {"value": world * batch * e2e_steps / float(t2.item()), "unit": "solves/s",
+               "h2d_bytes_per_step": int(a_h.nbytes + b_h.nbytes), "d2h_bytes_per_step": int(batch * n * 4),
+               "steps": e2e_steps, "api": "torch.func.vmap(lineax_b200.linear_solve(..., CG))"}
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    peak, peak_src = measured_peaks()
+    avg_launch_s = float(np.mean(per_launch_ms)) * 1e-3
+    achieved = alg_bytes / avg_launch_s / 1e9
+    traffic = None
+    tp = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tp):
+        traffic = json.load(open(tp)).get(args.workload)
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": traffic, "kernel": kernel_name, "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": alg_bytes, "avg_launch_ms": avg_launch_s * 1e3}
+
+    cpu_baseline = None
+    if world == 1 and not args.no_cpu_baseline:
+        cores = os.cpu_count() or 1
+        if args.workload == "lu32":
+            sa, sb = a_h, b_h
+            used = cores
+        else:
+            sa, sb = a_h[:64], b_h[:64]
+            used = 1
+        cpu_port_step(args.workload, sa[:64], sb[:64])
+        t0 = time.perf_counter()
+        done = 0
+        while time.perf_counter() - t0 < 10.0:
+            done += cpu_port_step(args.workload, sa, sb)
+        dt = time.perf_counter() - t0
+        cpu_baseline = {"value": done / dt, "unit": "solves/s", "cores": used, "kind": "port",
+                        "sample": f"{done} solves in {dt:.1f}s: oracle port of the same workload "
+                                  f"({sa.shape[0]} systems per pass); lineax/JAX itself is not installable here"}
+
+    line = {
+        "metric": f"batched solves/sec ({w['desc']})", "value": value, "unit": "solves/s", "n_gpus": world,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": total_ms_max / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": args.workload, "batch_per_gpu": batch, "n": n,
+                   "parallelism": f"batch-sharded x{world}, no collective",
+                   "l2": "inputs (%.0f MB per step) larger than the 126 MB L2" % ((a_h.nbytes + b_h.nbytes) / 1e6)},
+        "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline,
+        "cpu_baseline": cpu_baseline,
+    }
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,159 @@
+/*
+ * lineax_b200 -- C ABI of the B200-native solve hot path.
+ *
+ * The reference (patrick-kidger/lineax) has no FFI today: its seam is the Python
+ * ABC `AbstractLinearSolver` (lineax/_solve.py:343-480) whose `init` / `compute`
+ * are invoked at lineax/_solve.py:790 and lineax/_solve.py:98.  Every entry point
+ * below replaces the body of one of those methods for materialised operators and
+ * is what an XLA-FFI (`jax.ffi`) handler or the ctypes binding in
+ * lineax_b200/_native.py forwards to 1:1.
+ *
+ * Conventions
+ *  - All pointers are DEVICE pointers unless the name ends in `_host`.
+ *  - Matrices are row-major; `batch` independent systems are laid out with an
+ *    element stride between consecutive systems (`stride_*`, 0 = broadcast the
+ *    same operand to every system -- the vmap(in_axes=None) case).
+ *  - The caller owns every buffer; the library never allocates or frees device
+ *    memory and keeps no global state.  Calls are stream-ordered and never
+ *    synchronise the device.
+ *  - Return value: 0 ok; <0 bad argument (LXB_E_*); >0 a cudaError_t.
+ *    Numerical failure is DATA (`result[]` holds lineax RESULTS codes,
+ *    lineax/_solution.py:52-68), never a return code.
+ *  - `result[]` codes are the solver's own verdict (what `compute` returns);
+ *    the non-finite rewriting of lineax/_solve.py:104-123 is applied by
+ *    lxb_postprocess_* (or fused, where stated).
+ */
+#ifndef LINEAX_B200_H_
+#define LINEAX_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct CUstream_st* lxb_stream_t; /* == cudaStream_t */
+
+/* RESULTS codes, lineax/_solution.py:52-68 (definition order). */
+enum {
+  LXB_SUCCESSFUL = 0,
+  LXB_MAX_STEPS_REACHED = 1,
+  LXB_SINGULAR = 2,
+  LXB_BREAKDOWN = 3,
+  LXB_STAGNATION = 4,
+  LXB_CONLIM = 5,
+  LXB_NONFINITE_INPUT = 6
+};
+
+/* Argument errors. */
+enum {
+  LXB_E_BADARG = -1,      /* null pointer / negative size */
+  LXB_E_UNSUPPORTED = -2, /* shape outside what the kernels cover */
+  LXB_E_WORKSPACE = -3,   /* workspace too small */
+  LXB_E_ALIGN = -4        /* pointer/stride alignment requirement violated */
+};
+
+/* flags */
+enum {
+  LXB_TRANS = 1 << 0,          /* solve with the transposed operator (lu.py:62, qr.py:74) */
+  LXB_NSD = 1 << 1,            /* operator is negative definite: solve with -A, negate x (cg.py:100,224) */
+  LXB_MAXSTEPS_GIVEN = 1 << 2, /* max_steps was not None (selects max_steps_reached vs singular, cg.py:213-222) */
+  LXB_X64_BREAKDOWN = 1 << 3,  /* BiCGStab: `== 0` breakdown test (jax_enable_x64), bicgstab.py:110-113 */
+  LXB_HAS_Y0 = 1 << 4,         /* x holds the initial guess on entry (options["y0"]) */
+  LXB_UNIT_DIAG = 1 << 5,      /* triangular solve: unit diagonal */
+  LXB_LOWER = 1 << 6           /* triangular solve: lower triangular */
+};
+
+int lxb_version(void);
+const char* lxb_error_string(int code);
+/* Number of kernels this library has launched in this process (bench `gpu_launches`). */
+int64_t lxb_launch_count(void);
+
+/* ------------------------------------------------------------------ LU --
+ * lineax/_solver/lu.py:43-66.  `piv` is LAPACK getrf's row-swap sequence,
+ * 0-based int32 (jax.scipy.linalg.lu_factor convention).
+ * factor      : init()      A[batch,n,n] -> lu[batch,n,n], piv[batch,n]
+ * solve       : compute()   x = lu_solve((lu,piv), b, trans)
+ * factor_solve: init+compute fused, A is read once; lu/piv may be NULL (state not kept).
+ */
+#define LXB_DECL_LU(sfx, T)                                                                      \
+  int lxb_lu_factor_##sfx(const T* A, int64_t stride_A, T* lu, int32_t* piv, int64_t batch,      \
+                          int32_t n, lxb_stream_t stream);                                       \
+  int lxb_lu_solve_##sfx(const T* lu, int64_t stride_lu, const int32_t* piv, int64_t stride_piv, \
+                         const T* b, int64_t stride_b, T* x, int64_t batch, int32_t n,           \
+                         int32_t flags, lxb_stream_t stream);                                    \
+  int lxb_lu_factor_solve_##sfx(const T* A, int64_t stride_A, const T* b, int64_t stride_b,      \
+                                T* x, T* lu, int32_t* piv, int64_t batch, int32_t n,             \
+                                lxb_stream_t stream);
+LXB_DECL_LU(f32, float)
+LXB_DECL_LU(f64, double)
+
+/* ---------------------------------------------------------- Krylov ------
+ * One persistent fused kernel per batch of systems (matvec + dots + axpys +
+ * convergence/breakdown tests, no host round trips).
+ *   A[batch,n,n] row-major (lsmr: A[batch,m,n]); b[batch,n]; x[batch,n].
+ *   Minv: optional dense preconditioner [batch,n,n] (options["preconditioner"],
+ *         _solver/misc.py:30-60) or NULL for the identity.
+ *   x: output; with LXB_HAS_Y0 also the initial guess on entry.
+ *   result[batch] int32 RESULTS code; num_steps[batch] int32.
+ *   max_steps: already resolved by the caller (10*n when None, cg.py:124-127).
+ *   workspace: lxb_<solver>_workspace_<sfx>() bytes, only needed for systems
+ *              too large to keep their vectors on chip (may be NULL/0 otherwise).
+ */
+#define LXB_DECL_CG(sfx, T)                                                                        \
+  int lxb_cg_##sfx(const T* A, int64_t stride_A, const T* b, int64_t stride_b, const T* Minv,      \
+                   int64_t stride_M, T* x, int32_t* result, int32_t* num_steps, int64_t batch,     \
+                   int32_t n, T rtol, T atol, int32_t max_steps, int32_t stabilise_every,          \
+                   int32_t flags, void* workspace, size_t workspace_bytes, lxb_stream_t stream);   \
+  size_t lxb_cg_workspace_##sfx(int64_t batch, int32_t n);
+LXB_DECL_CG(f32, float)
+LXB_DECL_CG(f64, double)
+
+/* ------------------------------------------------ operator application --
+ * MatrixLinearOperator.mv (lineax/_operator.py:265-269; LXB_TRANS -> A^T x),
+ * DiagonalLinearOperator.mv (507-511), TridiagonalLinearOperator.mv (861-866;
+ * dl/du hold n-1 entries per system, stride_diag counts the diagonal's n) and the
+ * vector kernels of lineax/_norm.py:27-139: out[batch,3] = {two_norm(x), max_norm(x),
+ * dot(x, y) (0 when y is NULL)}.
+ */
+#define LXB_DECL_VEC(sfx, T)                                                                      \
+  int lxb_matvec_##sfx(const T* A, int64_t stride_A, const T* x, int64_t stride_x, T* y,          \
+                       int64_t batch, int32_t m, int32_t n, int32_t flags, lxb_stream_t stream);  \
+  int lxb_diag_mv_##sfx(const T* d, int64_t stride_d, const T* x, int64_t stride_x, T* y,         \
+                        int64_t batch, int32_t n, lxb_stream_t stream);                           \
+  int lxb_tridiag_mv_##sfx(const T* d, const T* dl, const T* du, int64_t stride_diag,             \
+                           const T* x, int64_t stride_x, T* y, int64_t batch, int32_t n,          \
+                           lxb_stream_t stream);                                                  \
+  int lxb_norms_##sfx(const T* x, int64_t stride_x, const T* y, int64_t stride_y, T* out,         \
+                      int64_t batch, int64_t n, lxb_stream_t stream);
+LXB_DECL_VEC(f32, float)
+LXB_DECL_VEC(f64, double)
+
+/* ------------------------------------------------------ post-processing --
+ * lineax/_solve.py:104-123, per system:
+ *   successful & any(!isfinite(x)) -> singular;  singular & any(!isfinite(b)) -> nonfinite_input.
+ * result[] is updated in place.
+ */
+#define LXB_DECL_POST(sfx, T)                                                                     \
+  int lxb_postprocess_##sfx(const T* x, int64_t stride_x, int32_t nx, const T* b,                 \
+                            int64_t stride_b, int32_t nb, int32_t* result, int64_t batch,         \
+                            lxb_stream_t stream);
+LXB_DECL_POST(f32, float)
+LXB_DECL_POST(f64, double)
+
+/* ------------------------------------------------- host-buffer entries --
+ * Same computation with HOST pointers: the library stages the batch through
+ * device scratch in chunks on internal streams (H2D copy / kernel / D2H copy
+ * overlapped).  `device_scratch` (lxb_host_scratch_bytes) is caller-owned
+ * device memory.  These are what `bench.py`'s e2e leg times.
+ */
+int lxb_lu_factor_solve_f32_host(const float* A_host, const float* b_host, float* x_host,
+                                 int64_t batch, int32_t n, void* device_scratch,
+                                 size_t scratch_bytes, lxb_stream_t stream);
+size_t lxb_host_scratch_bytes(int64_t batch, int32_t n, int32_t elem_bytes);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LINEAX_B200_H_ */

@@ -1,0 +1,140 @@
+"""CG parity (GPU): fused persistent kernel vs the NumPy restatement of lineax/_solver/cg.py:114-227.
+Tolerances (north_star): x within 1e-5 (fp32) / 1e-12 (fp64) relative, num_steps within +-2,
+RESULTS codes equal."""
+import numpy as np
+import pytest
+import torch
+
+import oracle
+from oracle import gen
+from tests.helpers import assert_close, dev, host
+
+pytestmark = pytest.mark.gpu
+
+MAXSTEPS_GIVEN, NSD = 4, 2
+
+
+def run_cg(a, b, rtol, atol, max_steps=None, stabilise_every=10, nsd=False, precond=None, y0=None):
+    from lineax_b200 import _ops
+
+    n = a.shape[-1]
+    ms = 10 * n if max_steps is None else max_steps
+    flags = (NSD if nsd else 0) | (0 if max_steps is None else MAXSTEPS_GIVEN)
+    se = 0 if stabilise_every is None else stabilise_every
+    x, res, steps = _ops.cg(dev(a), dev(b), None if precond is None else dev(precond),
+                            None if y0 is None else dev(y0), float(rtol), float(atol), ms, se, flags)
+    return host(x), host(res), host(steps)
+
+
+def oracle_batch(a, b, rtol, atol, **kw):
+    xs, rs, ss = [], [], []
+    pre, y0 = kw.pop("preconditioner", None), kw.pop("y0", None)
+    for i in range(a.shape[0]):
+        x, r, st = oracle.cg(a[i], b[i], rtol, atol,
+                             preconditioner=None if pre is None else pre[i],
+                             y0=None if y0 is None else y0[i], **kw)
+        xs.append(x), rs.append(r), ss.append(st["num_steps"])
+    return np.stack(xs), np.array(rs), np.array(ss)
+
+
+@pytest.mark.parametrize("n", [1, 3, 17, 64, 100, 128, 256, 300])
+@pytest.mark.parametrize("dtype,tol", [(np.float32, 1e-6), (np.float64, 1e-12)])
+def test_easy_spd(n, dtype, tol):
+    a, b, _ = gen.easy_problem(n, n, dtype, spd=True, batch=9)
+    x, res, steps = run_cg(a, b, tol, tol)
+    xr, rr, sr = oracle_batch(a, b, tol, tol)
+    assert np.array_equal(res, rr)
+    assert np.all(np.abs(steps - sr) <= 2), (steps, sr)
+    assert_close(x, xr, dtype, factor=4)
+
+
+@pytest.mark.parametrize("cond,expect", [(3, 13), (10, 24), (30, 47)])
+def test_spectrum_c3_secondary(cond, expect):
+    """SURVEY 8(d) C3 secondary generator: iteration counts of the reference algorithm."""
+    a, b, _ = gen.spectrum_spd(11, 256, cond, np.float32, batch=4)
+    x, res, steps = run_cg(a, b, 1e-6, 1e-6)
+    xr, rr, sr = oracle_batch(a, b, 1e-6, 1e-6)
+    assert np.array_equal(res, rr) and np.all(res == 0)
+    assert np.all(np.abs(steps - sr) <= 2), (steps, sr)
+    assert np.all(np.abs(sr - expect) <= 3)
+    assert_close(x, xr, np.float32, factor=10)
+
+
+def test_c1_config_fp64_1024():
+    """BASELINE configs[0]: CG on 1024^2 dense SPD fp64, single RHS."""
+    a, b, xt = gen.easy_problem(1, 1024, np.float64, spd=True)
+    x, res, steps = run_cg(a[None], b[None], 1e-12, 1e-12)
+    xr, rr, st = oracle.cg(a, b, 1e-12, 1e-12)
+    assert res[0] == rr == 0 and abs(int(steps[0]) - st["num_steps"]) <= 2
+    assert_close(x[0], xr, np.float64, factor=4)
+    assert_close(x[0], xt, np.float64, factor=1e3)
+
+
+def test_negative_definite_and_stabilise_variants():
+    a, b, _ = gen.easy_problem(3, 50, np.float64, spd=True, batch=4)
+    for se in (None, 1, 3, 10):
+        x, res, steps = run_cg(-a, b, 1e-10, 1e-10, stabilise_every=se, nsd=True)
+        xr, rr, sr = oracle_batch(-a, b, 1e-10, 1e-10, stabilise_every=se, is_nsd=True)
+        assert np.array_equal(res, rr) and np.all(np.abs(steps - sr) <= 2)
+        assert_close(x, xr, np.float64, factor=100)
+
+
+def test_max_steps_only_poisson():
+    """tests/test_solve.py:174-194: rtol=atol=0, max_steps=2 on Poisson(100) -> successful."""
+    p = gen.poisson_matrix(100, np.float64)
+    rhs = np.random.default_rng(0).standard_normal(100)
+    x, res, steps = run_cg(p[None], rhs[None], 0.0, 0.0, max_steps=2, nsd=True)
+    xr, rr, st = oracle.cg(p, rhs, 0.0, 0.0, max_steps=2, is_nsd=True)
+    assert res[0] == rr == 0 and steps[0] == st["num_steps"] == 2
+    assert_close(x[0], xr, np.float64, factor=100)
+
+
+def test_max_steps_reached_and_singular_codes():
+    a, b, _ = gen.spectrum_spd(5, 64, 1e4, np.float64, batch=3)
+    x, res, steps = run_cg(a, b, 1e-14, 1e-14, max_steps=5)
+    xr, rr, sr = oracle_batch(a, b, 1e-14, 1e-14, max_steps=5)
+    assert np.array_equal(res, rr) and np.all(res == 1) and np.array_equal(steps, sr)
+
+
+def test_preconditioner_and_y0():
+    """tests/test_adjoint.py:84-130: exact-inverse preconditioner converges in <= 3 steps."""
+    rng = np.random.default_rng(123)
+    A = rng.uniform(size=(10, 10)) + np.diag(np.arange(10.0) ** 6)
+    A = A.T @ A
+    b = rng.uniform(size=10)
+    M = np.linalg.inv(A)
+    x, res, steps = run_cg(A[None], b[None], 1e-12, 1e-12, max_steps=3, precond=M[None])
+    xr, rr, st = oracle.cg(A, b, 1e-12, 1e-12, max_steps=3, preconditioner=M)
+    assert res[0] == rr and abs(int(steps[0]) - st["num_steps"]) <= 1
+    assert np.max(np.abs(x[0] - xr) / np.abs(xr).max()) < 1e-9
+    y0 = rng.standard_normal((1, 10))
+    x, res, steps = run_cg(A[None], b[None], 1e-12, 1e-12, y0=y0)
+    xr, rr, st = oracle.cg(A, b, 1e-12, 1e-12, y0=y0[0])
+    assert res[0] == rr
+
+
+def test_nonfinite_operator_trap():
+    """NaN in A poisons r0 -> gamma NaN -> zero steps, x = 0, 'successful'."""
+    a, b, _ = gen.easy_problem(0, 16, np.float32, spd=True, batch=2)
+    a[0, 3, 4] = np.nan
+    x, res, steps = run_cg(a, b, 1e-6, 1e-6)
+    xr, rr, sr = oracle_batch(a, b, 1e-6, 1e-6)
+    assert steps[0] == sr[0] == 0 and res[0] == rr[0] == 0 and np.all(x[0] == 0)
+    assert steps[1] == sr[1]
+
+
+def test_c3_full_size_properties():
+    """Full C3 size (4096 x 256^2 f32): residual property + step histogram vs oracle sample."""
+    a, b, xt = gen.easy_problem(3, 256, np.float32, spd=True, batch=64)
+    reps = 64
+    A = dev(a).repeat(reps, 1, 1)
+    B = dev(b).repeat(reps, 1)
+    from lineax_b200 import _ops
+
+    x, res, steps = _ops.cg(A, B, None, None, 1e-6, 1e-6, 2560, 10, 0)
+    x, res, steps = host(x), host(res), host(steps)
+    assert x.shape == (4096, 256) and np.all(res == 0)
+    xr, rr, sr = oracle_batch(a, b, 1e-6, 1e-6)
+    assert np.all(np.abs(steps.reshape(reps, 64) - sr[None]) <= 2)
+    assert np.array_equal(x[:64], x[64 * 63:]), "identical systems give identical answers"
+    assert_close(x[:64], xr, np.float32, factor=4)
