@@ -89,6 +89,66 @@ int64_t lxb_launch_count(void);
 LXB_DECL_LU(f32, float)
 LXB_DECL_LU(f64, double)
 
+/* ------------------------------------------------------------ Cholesky --
+ * lineax/_solver/cholesky.py:43-78.  factor = upper U with (+-A) = U^T U.
+ */
+#define LXB_DECL_CHOL(sfx, T)                                                                   \
+  int lxb_cholesky_factor_##sfx(const T* A, int64_t stride_A, T* factor, int64_t batch,         \
+                                int32_t n, int32_t flags, lxb_stream_t stream);                 \
+  int lxb_cholesky_solve_##sfx(const T* factor, int64_t stride_f, const T* b, int64_t stride_b, \
+                               T* x, int64_t batch, int32_t n, int32_t flags,                   \
+                               lxb_stream_t stream);
+LXB_DECL_CHOL(f32, float)
+LXB_DECL_CHOL(f64, double)
+
+/* ------------------------------------------------------------------ QR --
+ * lineax/_solver/qr.py:55-94.  `a`[batch,rows,cols] (rows >= cols) is geqrf's
+ * output (R above the diagonal, Householder vectors below), taus[batch,cols].
+ * factor: A[batch,m,n]; when n > m the routine factors A^T (qr.py:59-61), i.e.
+ *         rows = max(m,n), cols = min(m,n).
+ * solve : LXB_TRANS clear -> least squares  x[cols] = R^-1 (Q^T b[rows])[:cols]
+ *         LXB_TRANS set   -> minimum norm   x[rows] = Q [R^-T b[cols]; 0]
+ */
+#define LXB_DECL_QR(sfx, T)                                                                       \
+  int lxb_qr_factor_##sfx(const T* A, int64_t stride_A, T* a, T* taus, int64_t batch, int32_t m,  \
+                          int32_t n, void* workspace, size_t workspace_bytes,                     \
+                          lxb_stream_t stream);                                                   \
+  size_t lxb_qr_factor_workspace_##sfx(int64_t batch, int32_t m, int32_t n);                      \
+  int lxb_qr_solve_##sfx(const T* a, int64_t stride_a, const T* taus, int64_t stride_t,           \
+                         const T* b, int64_t stride_b, T* x, int64_t batch, int32_t rows,         \
+                         int32_t cols, int32_t flags, void* workspace, size_t workspace_bytes,    \
+                         lxb_stream_t stream);                                                    \
+  size_t lxb_qr_solve_workspace_##sfx(int64_t batch, int32_t rows, int32_t cols);
+LXB_DECL_QR(f32, float)
+LXB_DECL_QR(f64, double)
+
+/* ---------------------------------------------------------- Tridiagonal --
+ * lineax/_solver/tridiagonal.py:54-72.  d[batch,n], dl/du[batch,n-1]
+ * (dl = sub-diagonal, du = super-diagonal; the reference pads them itself at
+ * tridiagonal.py:65-67), b/x[batch,n].  Partial pivoting like LAPACK gtsv.
+ * workspace: lxb_tridiagonal_workspace_*() bytes of device scratch (L2-resident slab).
+ */
+#define LXB_DECL_TRIDIAG(sfx, T)                                                                 \
+  int lxb_tridiagonal_solve_##sfx(const T* d, const T* dl, const T* du, int64_t stride_diag,     \
+                                  const T* b, int64_t stride_b, T* x, int64_t batch, int32_t n,  \
+                                  void* workspace, size_t workspace_bytes, lxb_stream_t stream); \
+  size_t lxb_tridiagonal_workspace_##sfx(int64_t batch, int32_t n);
+LXB_DECL_TRIDIAG(f32, float)
+LXB_DECL_TRIDIAG(f64, double)
+
+/* -------------------------------------------- Diagonal / Triangular -----
+ * lineax/_solver/diagonal.py:66-83, triangular.py:68-85 (dispatch targets of
+ * AutoLinearSolver, _solve.py:555-600).  rcond < 0 selects the well-posed path.
+ */
+#define LXB_DECL_DIAGTRI(sfx, T)                                                                 \
+  int lxb_diagonal_solve_##sfx(const T* diag, int64_t stride_d, const T* b, int64_t stride_b,    \
+                               T* x, int64_t batch, int32_t n, T rcond, lxb_stream_t stream);    \
+  int lxb_triangular_solve_##sfx(const T* A, int64_t stride_A, const T* b, int64_t stride_b,     \
+                                 T* x, int64_t batch, int32_t n, int32_t flags,                  \
+                                 lxb_stream_t stream);
+LXB_DECL_DIAGTRI(f32, float)
+LXB_DECL_DIAGTRI(f64, double)
+
 /* ---------------------------------------------------------- Krylov ------
  * One persistent fused kernel per batch of systems (matvec + dots + axpys +
  * convergence/breakdown tests, no host round trips).
@@ -101,14 +161,32 @@ LXB_DECL_LU(f64, double)
  *   workspace: lxb_<solver>_workspace_<sfx>() bytes, only needed for systems
  *              too large to keep their vectors on chip (may be NULL/0 otherwise).
  */
-#define LXB_DECL_CG(sfx, T)                                                                        \
+#define LXB_DECL_KRYLOV(sfx, T)                                                                    \
   int lxb_cg_##sfx(const T* A, int64_t stride_A, const T* b, int64_t stride_b, const T* Minv,      \
                    int64_t stride_M, T* x, int32_t* result, int32_t* num_steps, int64_t batch,     \
                    int32_t n, T rtol, T atol, int32_t max_steps, int32_t stabilise_every,          \
                    int32_t flags, void* workspace, size_t workspace_bytes, lxb_stream_t stream);   \
-  size_t lxb_cg_workspace_##sfx(int64_t batch, int32_t n);
-LXB_DECL_CG(f32, float)
-LXB_DECL_CG(f64, double)
+  size_t lxb_cg_workspace_##sfx(int64_t batch, int32_t n);                                         \
+  int lxb_bicgstab_##sfx(const T* A, int64_t stride_A, const T* b, int64_t stride_b,               \
+                         const T* Minv, int64_t stride_M, T* x, int32_t* result,                   \
+                         int32_t* num_steps, int64_t batch, int32_t n, T rtol, T atol,             \
+                         int32_t max_steps, int32_t flags, void* workspace,                        \
+                         size_t workspace_bytes, lxb_stream_t stream);                             \
+  size_t lxb_bicgstab_workspace_##sfx(int64_t batch, int32_t n);                                   \
+  int lxb_gmres_##sfx(const T* A, int64_t stride_A, const T* b, int64_t stride_b, const T* Minv,   \
+                      int64_t stride_M, T* x, int32_t* result, int32_t* num_steps, int64_t batch,  \
+                      int32_t n, T rtol, T atol, int32_t max_steps, int32_t restart,               \
+                      int32_t stagnation_iters, int32_t flags, void* workspace,                    \
+                      size_t workspace_bytes, lxb_stream_t stream);                                \
+  size_t lxb_gmres_workspace_##sfx(int64_t batch, int32_t n, int32_t restart);                     \
+  /* stats[batch,8]: istop, norm_r, norm_Ar, norm_A, cond_A, norm_x, 0, 0 (lsmr.py:334-342) */     \
+  int lxb_lsmr_##sfx(const T* A, int64_t stride_A, const T* b, int64_t stride_b, T* x,             \
+                     int32_t* result, int32_t* num_steps, T* stats, int64_t batch, int32_t m,      \
+                     int32_t n, T rtol, T atol, T conlim, int64_t max_steps, int32_t flags,        \
+                     void* workspace, size_t workspace_bytes, lxb_stream_t stream);                \
+  size_t lxb_lsmr_workspace_##sfx(int64_t batch, int32_t m, int32_t n);
+LXB_DECL_KRYLOV(f32, float)
+LXB_DECL_KRYLOV(f64, double)
 
 /* ------------------------------------------------ operator application --
  * MatrixLinearOperator.mv (lineax/_operator.py:265-269; LXB_TRANS -> A^T x),

@@ -66,6 +66,36 @@ for _sfx, _T in (("f32", c_float), ("f64", c_double)):
     _decl(f"lxb_diag_mv_{_sfx}", [P, c_int64, P, c_int64, P, c_int64, c_int32, P])
     _decl(f"lxb_tridiag_mv_{_sfx}", [P, P, P, c_int64, P, c_int64, P, c_int64, c_int32, P])
     _decl(f"lxb_norms_{_sfx}", [P, c_int64, P, c_int64, P, c_int64, c_int64, P])
+    _decl(f"lxb_cholesky_factor_{_sfx}", [P, c_int64, P, c_int64, c_int32, c_int32, P])
+    _decl(f"lxb_cholesky_solve_{_sfx}", [P, c_int64, P, c_int64, P, c_int64, c_int32, c_int32, P])
+    _decl(f"lxb_qr_factor_{_sfx}", [P, c_int64, P, P, c_int64, c_int32, c_int32, P, c_size_t, P])
+    _decl(f"lxb_qr_factor_workspace_{_sfx}", [c_int64, c_int32, c_int32], c_size_t)
+    _decl(f"lxb_qr_solve_{_sfx}",
+          [P, c_int64, P, c_int64, P, c_int64, P, c_int64, c_int32, c_int32, c_int32, P, c_size_t, P])
+    _decl(f"lxb_qr_solve_workspace_{_sfx}", [c_int64, c_int32, c_int32], c_size_t)
+    _decl(f"lxb_tridiagonal_solve_{_sfx}",
+          [P, P, P, c_int64, P, c_int64, P, c_int64, c_int32, P, c_size_t, P])
+    _decl(f"lxb_tridiagonal_workspace_{_sfx}", [c_int64, c_int32], c_size_t)
+    _decl(f"lxb_diagonal_solve_{_sfx}", [P, c_int64, P, c_int64, P, c_int64, c_int32, _T, P])
+    _decl(f"lxb_triangular_solve_{_sfx}", [P, c_int64, P, c_int64, P, c_int64, c_int32, c_int32, P])
+    _decl(
+        f"lxb_bicgstab_{_sfx}",
+        [P, c_int64, P, c_int64, P, c_int64, P, P, P, c_int64, c_int32, _T, _T, c_int32, c_int32, P,
+         c_size_t, P],
+    )
+    _decl(f"lxb_bicgstab_workspace_{_sfx}", [c_int64, c_int32], c_size_t)
+    _decl(
+        f"lxb_gmres_{_sfx}",
+        [P, c_int64, P, c_int64, P, c_int64, P, P, P, c_int64, c_int32, _T, _T, c_int32, c_int32,
+         c_int32, c_int32, P, c_size_t, P],
+    )
+    _decl(f"lxb_gmres_workspace_{_sfx}", [c_int64, c_int32, c_int32], c_size_t)
+    _decl(
+        f"lxb_lsmr_{_sfx}",
+        [P, c_int64, P, c_int64, P, P, P, P, c_int64, c_int32, c_int32, _T, _T, _T, c_int64, c_int32,
+         P, c_size_t, P],
+    )
+    _decl(f"lxb_lsmr_workspace_{_sfx}", [c_int64, c_int32, c_int32], c_size_t)
 _decl("lxb_lu_factor_solve_f32_host", [P, P, P, c_int64, c_int32, P, c_size_t, P])
 _decl("lxb_host_scratch_bytes", [c_int64, c_int32, c_int32], c_size_t)
 

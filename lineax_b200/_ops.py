@@ -299,3 +299,214 @@ def _dot(x: Tensor, y: Tensor) -> Tensor:
 
 
 dot = _define("dot", _dot, n_out=1)
+
+
+# ------------------------------------------------------------ other Krylov ----
+def _krylov_common(a, b, precond, y0, core_a=2):
+    _check_cuda(a, b, precond, y0)
+    full = _full_batch((a, core_a), (b, 1), (precond, 2), (y0, 1))
+    return full, math.prod(full), nat.suffix(a.dtype)
+
+
+def _bicgstab(a: Tensor, b: Tensor, precond: Optional[Tensor], y0: Optional[Tensor], rtol: float,
+              atol: float, max_steps: int, flags: int) -> Tuple[Tensor, Tensor, Tensor]:
+    n = a.shape[-1]
+    full, B, sfx = _krylov_common(a, b, precond, y0)
+    with torch.cuda.device(a.device):
+        a_, s_a = _operand(a, 2, full)
+        b_, s_b = _operand(b.to(a.dtype), 1, full)
+        m_, s_m = (None, 0) if precond is None else _operand(precond.to(a.dtype), 2, full)
+        if y0 is not None:
+            x = y0.to(a.dtype).expand(full + (n,)).contiguous().clone()
+            flags |= nat.HAS_Y0
+        else:
+            x = torch.empty(full + (n,), dtype=a.dtype, device=a.device)
+        result = torch.empty(full, dtype=torch.int32, device=a.device)
+        steps = torch.empty(full, dtype=torch.int32, device=a.device)
+        nat.call(f"lxb_bicgstab_{sfx}", a_.data_ptr(), s_a, b_.data_ptr(), s_b, _ptr(m_), s_m,
+                 x.data_ptr(), result.data_ptr(), steps.data_ptr(), B, n, rtol, atol, max_steps, flags,
+                 None, 0, _stream())
+    return x, result, steps
+
+
+bicgstab = _define("bicgstab", _bicgstab, n_out=3)
+
+
+def _gmres(a: Tensor, b: Tensor, precond: Optional[Tensor], y0: Optional[Tensor], rtol: float,
+           atol: float, max_steps: int, restart: int, stagnation_iters: int,
+           flags: int) -> Tuple[Tensor, Tensor, Tensor]:
+    n = a.shape[-1]
+    full, B, sfx = _krylov_common(a, b, precond, y0)
+    with torch.cuda.device(a.device):
+        a_, s_a = _operand(a, 2, full)
+        b_, s_b = _operand(b.to(a.dtype), 1, full)
+        m_, s_m = (None, 0) if precond is None else _operand(precond.to(a.dtype), 2, full)
+        if y0 is not None:
+            x = y0.to(a.dtype).expand(full + (n,)).contiguous().clone()
+            flags |= nat.HAS_Y0
+        else:
+            x = torch.empty(full + (n,), dtype=a.dtype, device=a.device)
+        result = torch.empty(full, dtype=torch.int32, device=a.device)
+        steps = torch.empty(full, dtype=torch.int32, device=a.device)
+        ws_bytes = nat.fn(f"lxb_gmres_workspace_{sfx}")(B, n, restart)
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=a.device) if ws_bytes else None
+        nat.call(f"lxb_gmres_{sfx}", a_.data_ptr(), s_a, b_.data_ptr(), s_b, _ptr(m_), s_m, x.data_ptr(),
+                 result.data_ptr(), steps.data_ptr(), B, n, rtol, atol, max_steps, restart,
+                 stagnation_iters, flags, _ptr(ws), ws_bytes, _stream())
+    return x, result, steps
+
+
+gmres = _define("gmres", _gmres, n_out=3)
+
+
+def _lsmr(a: Tensor, b: Tensor, y0: Optional[Tensor], rtol: float, atol: float, conlim: float,
+          max_steps: int, flags: int) -> Tuple[Tensor, Tensor, Tensor, Tensor]:
+    _check_cuda(a, b, y0)
+    m, n = a.shape[-2], a.shape[-1]
+    full = _full_batch((a, 2), (b, 1), (y0, 1))
+    B = math.prod(full)
+    sfx = nat.suffix(a.dtype)
+    with torch.cuda.device(a.device):
+        a_, s_a = _operand(a, 2, full)
+        b_, s_b = _operand(b.to(a.dtype), 1, full)
+        if y0 is not None:
+            x = y0.to(a.dtype).expand(full + (n,)).contiguous().clone()
+            flags |= nat.HAS_Y0
+        else:
+            x = torch.empty(full + (n,), dtype=a.dtype, device=a.device)
+        result = torch.empty(full, dtype=torch.int32, device=a.device)
+        steps = torch.empty(full, dtype=torch.int32, device=a.device)
+        stats = torch.empty(full + (8,), dtype=a.dtype, device=a.device)
+        nat.call(f"lxb_lsmr_{sfx}", a_.data_ptr(), s_a, b_.data_ptr(), s_b, x.data_ptr(),
+                 result.data_ptr(), steps.data_ptr(), stats.data_ptr(), B, m, n, rtol, atol, conlim,
+                 max_steps, flags, None, 0, _stream())
+    return x, result, steps, stats
+
+
+lsmr = _define("lsmr", _lsmr, n_out=4)
+
+
+# ------------------------------------------------------------ other direct ----
+def _cholesky_factor(a: Tensor, nsd: bool) -> Tensor:
+    _check_cuda(a)
+    n = a.shape[-1]
+    full = _batch(a, 2)
+    sfx = nat.suffix(a.dtype)
+    with torch.cuda.device(a.device):
+        a_ = a.contiguous()
+        f = torch.empty_like(a_)
+        nat.call(f"lxb_cholesky_factor_{sfx}", a_.data_ptr(), n * n, f.data_ptr(), math.prod(full), n,
+                 nat.NSD if nsd else 0, _stream())
+    return f
+
+
+def _cholesky_solve(f: Tensor, b: Tensor, nsd: bool) -> Tensor:
+    _check_cuda(f, b)
+    n = f.shape[-1]
+    full = _full_batch((f, 2), (b, 1))
+    sfx = nat.suffix(f.dtype)
+    with torch.cuda.device(f.device):
+        f_, s_f = _operand(f, 2, full)
+        b_, s_b = _operand(b.to(f.dtype), 1, full)
+        x = torch.empty(full + (n,), dtype=f.dtype, device=f.device)
+        nat.call(f"lxb_cholesky_solve_{sfx}", f_.data_ptr(), s_f, b_.data_ptr(), s_b, x.data_ptr(),
+                 math.prod(full), n, nat.NSD if nsd else 0, _stream())
+    return x
+
+
+cholesky_factor = _define("cholesky_factor", _cholesky_factor, n_out=1)
+cholesky_solve = _define("cholesky_solve", _cholesky_solve, n_out=1)
+
+
+def _qr_factor(a: Tensor) -> Tuple[Tensor, Tensor]:
+    _check_cuda(a)
+    m, n = a.shape[-2], a.shape[-1]
+    rows, cols = max(m, n), min(m, n)
+    full = _batch(a, 2)
+    sfx = nat.suffix(a.dtype)
+    with torch.cuda.device(a.device):
+        a_ = a.contiguous()
+        out = torch.empty(full + (rows, cols), dtype=a.dtype, device=a.device)
+        taus = torch.empty(full + (cols,), dtype=a.dtype, device=a.device)
+        nat.call(f"lxb_qr_factor_{sfx}", a_.data_ptr(), m * n, out.data_ptr(), taus.data_ptr(),
+                 math.prod(full), m, n, None, 0, _stream())
+    return out, taus
+
+
+def _qr_solve(a: Tensor, taus: Tensor, b: Tensor, trans: bool) -> Tensor:
+    _check_cuda(a, taus, b)
+    rows, cols = a.shape[-2], a.shape[-1]
+    full = _full_batch((a, 2), (taus, 1), (b, 1))
+    sfx = nat.suffix(a.dtype)
+    with torch.cuda.device(a.device):
+        a_, s_a = _operand(a, 2, full)
+        t_, s_t = _operand(taus, 1, full)
+        b_, s_b = _operand(b.to(a.dtype), 1, full)
+        x = torch.empty(full + ((rows if trans else cols),), dtype=a.dtype, device=a.device)
+        nat.call(f"lxb_qr_solve_{sfx}", a_.data_ptr(), s_a, t_.data_ptr(), s_t, b_.data_ptr(), s_b,
+                 x.data_ptr(), math.prod(full), rows, cols, nat.TRANS if trans else 0, None, 0, _stream())
+    return x
+
+
+qr_factor = _define("qr_factor", _qr_factor, n_out=2)
+qr_solve = _define("qr_solve", _qr_solve, n_out=1)
+
+
+def _tridiagonal_solve(d: Tensor, dl: Tensor, du: Tensor, b: Tensor) -> Tensor:
+    _check_cuda(d, dl, du, b)
+    n = d.shape[-1]
+    full = _full_batch((d, 1), (dl, 1), (du, 1), (b, 1))
+    B = math.prod(full)
+    sfx = nat.suffix(d.dtype)
+    with torch.cuda.device(d.device):
+        d_ = d.expand(full + (n,)).contiguous()
+        dl_ = dl.to(d.dtype).expand(full + (max(n - 1, 0),)).contiguous()
+        du_ = du.to(d.dtype).expand(full + (max(n - 1, 0),)).contiguous()
+        b_, s_b = _operand(b.to(d.dtype), 1, full)
+        x = torch.empty(full + (n,), dtype=d.dtype, device=d.device)
+        ws_bytes = nat.fn(f"lxb_tridiagonal_workspace_{sfx}")(B, n)
+        ws = torch.empty(max(ws_bytes, 16), dtype=torch.uint8, device=d.device)
+        nat.call(f"lxb_tridiagonal_solve_{sfx}", d_.data_ptr(), dl_.data_ptr() if n > 1 else None,
+                 du_.data_ptr() if n > 1 else None, n, b_.data_ptr(), s_b, x.data_ptr(), B, n,
+                 ws.data_ptr(), ws_bytes, _stream())
+    return x
+
+
+tridiagonal_solve = _define("tridiagonal_solve", _tridiagonal_solve, n_out=1)
+
+
+def _diagonal_solve(d: Tensor, b: Tensor, rcond: float) -> Tensor:
+    _check_cuda(d, b)
+    n = d.shape[-1]
+    full = _full_batch((d, 1), (b, 1))
+    dt = torch.promote_types(d.dtype, b.dtype)
+    sfx = nat.suffix(dt)
+    with torch.cuda.device(d.device):
+        d_, s_d = _operand(d.to(dt), 1, full)
+        b_, s_b = _operand(b.to(dt), 1, full)
+        x = torch.empty(full + (n,), dtype=dt, device=d.device)
+        nat.call(f"lxb_diagonal_solve_{sfx}", d_.data_ptr(), s_d, b_.data_ptr(), s_b, x.data_ptr(),
+                 math.prod(full), n, rcond, _stream())
+    return x
+
+
+diagonal_solve = _define("diagonal_solve", _diagonal_solve, n_out=1)
+
+
+def _triangular_solve(a: Tensor, b: Tensor, lower: bool, unit: bool, trans: bool) -> Tensor:
+    _check_cuda(a, b)
+    n = a.shape[-1]
+    full = _full_batch((a, 2), (b, 1))
+    dt = torch.promote_types(a.dtype, b.dtype)
+    sfx = nat.suffix(dt)
+    flags = (nat.LOWER if lower else 0) | (nat.UNIT_DIAG if unit else 0) | (nat.TRANS if trans else 0)
+    with torch.cuda.device(a.device):
+        a_, s_a = _operand(a.to(dt), 2, full)
+        b_, s_b = _operand(b.to(dt), 1, full)
+        x = torch.empty(full + (n,), dtype=dt, device=a.device)
+        nat.call(f"lxb_triangular_solve_{sfx}", a_.data_ptr(), s_a, b_.data_ptr(), s_b, x.data_ptr(),
+                 math.prod(full), n, flags, _stream())
+    return x
+
+
+triangular_solve = _define("triangular_solve", _triangular_solve, n_out=1)

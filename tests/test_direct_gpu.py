@@ -1,0 +1,139 @@
+"""Cholesky / QR / Tridiagonal / Diagonal / Triangular parity (GPU) vs the SciPy-LAPACK oracle."""
+import numpy as np
+import pytest
+
+import oracle
+from oracle import gen
+from tests.helpers import assert_close, dev, host
+
+pytestmark = pytest.mark.gpu
+
+
+def _ops():
+    from lineax_b200 import _ops
+
+    return _ops
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+@pytest.mark.parametrize("n", [1, 2, 5, 32, 64, 150, 250])
+@pytest.mark.parametrize("nsd", [False, True])
+def test_cholesky(n, dtype, nsd):
+    a, b, _ = gen.easy_problem(n, n, dtype, spd=True, batch=4)
+    if nsd:
+        a = -a
+    f = _ops().cholesky_factor(dev(a), nsd)
+    x = _ops().cholesky_solve(f, dev(b), nsd)
+    for i in range(4):
+        st = oracle.cholesky_init(a[i], is_nsd=nsd)
+        assert_close(np.triu(host(f)[i]), np.triu(st[0]), dtype, factor=50 * n)
+        assert np.all(np.tril(host(f)[i], -1) == 0)
+        assert_close(host(x)[i], oracle.cholesky_compute(st, b[i]), dtype, factor=100 * n)
+
+
+def test_cholesky_not_pd_gives_nan():
+    a = np.array([[[1.0, 2.0], [2.0, 1.0]]], np.float32)
+    f = host(_ops().cholesky_factor(dev(a), False))
+    assert np.all(np.isnan(f))
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+@pytest.mark.parametrize("shape", [(1, 1), (3, 3), (5, 3), (3, 5), (21, 20), (64, 64), (500, 200), (200, 500), (2048, 16)])
+def test_qr(shape, dtype):
+    m, n = shape
+    rng = np.random.default_rng(m * 7 + n)
+    a = rng.standard_normal((3, m, n)).astype(dtype)
+    b = rng.standard_normal((3, m)).astype(dtype)
+    aq, taus = _ops().qr_factor(dev(a))
+    x = host(_ops().qr_solve(aq, taus, dev(b), n > m))
+    for i in range(3):
+        st = oracle.qr_init(a[i])
+        xr = oracle.qr_compute(st, b[i])
+        assert_close(x[i], xr, dtype, factor=200 * max(m, n))
+        xl = np.linalg.lstsq(a[i].astype(np.float64), b[i].astype(np.float64), rcond=None)[0]
+        assert np.max(np.abs(x[i] - xl)) / np.abs(xl).max() < (1e-3 if dtype == np.float32 else 1e-9)
+        (a_ref, taus_ref), _ = st
+        rows, cols = a_ref.shape
+        # R and taus follow LAPACK's sign conventions (geqr2): compare directly
+        assert_close(np.triu(host(aq)[i][:cols]), np.triu(a_ref[:cols]), dtype, factor=500 * max(m, n))
+        assert_close(host(taus)[i], taus_ref, dtype, factor=500 * max(m, n))
+
+
+def test_qr_transposed_state():
+    """QR.transpose(): solving A^T x = b reuses the factors of A (qr.py:96-104)."""
+    rng = np.random.default_rng(3)
+    a = rng.standard_normal((1, 6, 4))
+    b = rng.standard_normal((1, 4))
+    aq, taus = _ops().qr_factor(dev(a))
+    x = host(_ops().qr_solve(aq, taus, dev(b), True))[0]  # min-norm solution of A^T x = b
+    xl = np.linalg.lstsq(a[0].T, b[0], rcond=None)[0]
+    assert np.max(np.abs(x - xl)) < 1e-10
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+@pytest.mark.parametrize("n", [1, 2, 3, 31, 32, 33, 100, 512, 700])
+def test_tridiagonal_dominant(n, dtype):
+    d, l, u, b = gen.tridiagonal_systems(n, 70, n, dtype)
+    x = host(_ops().tridiagonal_solve(dev(d), dev(l), dev(u), dev(b)))
+    for i in range(0, 70, 9):
+        xr = oracle.tridiagonal_compute(d[i], l[i], u[i], b[i])
+        assert_close(x[i], xr, dtype, factor=50)
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+@pytest.mark.parametrize("n", [2, 3, 10, 64, 200])
+def test_tridiagonal_general_needs_pivoting(n, dtype):
+    """Random (non-dominant) tridiagonals as in tests/helpers.py: pivoting path of gtsv."""
+    rng = np.random.default_rng(n)
+    d = rng.standard_normal((40, n)).astype(dtype)
+    l = rng.standard_normal((40, n - 1)).astype(dtype)
+    u = rng.standard_normal((40, n - 1)).astype(dtype)
+    b = rng.standard_normal((40, n)).astype(dtype)
+    x = host(_ops().tridiagonal_solve(dev(d), dev(l), dev(u), dev(b)))
+    for i in range(40):
+        T = np.diag(d[i]) + np.diag(l[i], -1) + np.diag(u[i], 1)
+        if np.linalg.cond(T.astype(np.float64)) > 1000:
+            continue
+        xr = oracle.tridiagonal_compute(d[i], l[i], u[i], b[i])
+        assert_close(x[i], xr, dtype, factor=2000)
+
+
+def test_tridiagonal_c5_properties():
+    """C5 tridiagonal shape at 2^16 systems x 512: residual property."""
+    d, l, u, b = gen.tridiagonal_systems(5, 1 << 16, 512, np.float32)
+    x = host(_ops().tridiagonal_solve(dev(d), dev(l), dev(u), dev(b)))
+    r = d * x - b
+    r[:, :-1] += u * x[:, 1:]
+    r[:, 1:] += l * x[:, :-1]
+    assert np.max(np.abs(r)) < 5e-5
+    xr = oracle.tridiagonal_compute(d[12345], l[12345], u[12345], b[12345])
+    assert_close(x[12345], xr, np.float32, factor=20)
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+def test_diagonal_and_triangular(dtype):
+    rng = np.random.default_rng(0)
+    d = rng.standard_normal((6, 17)).astype(dtype)
+    d[0, 3] = 0.0
+    d[1, :] *= 1e-12
+    d[1, 0] = 1.0
+    b = rng.standard_normal((6, 17)).astype(dtype)
+    eps = np.finfo(dtype).eps
+    x = host(_ops().diagonal_solve(dev(d), dev(b), float(2 * eps * 17)))
+    xw = host(_ops().diagonal_solve(dev(d), dev(b), -1.0))
+    for i in range(6):
+        assert_close(x[i], oracle.diagonal_compute(d[i], b[i]), dtype)
+        ref = oracle.diagonal_compute(d[i], b[i], well_posed=True)
+        fin = np.isfinite(ref)
+        assert np.array_equal(np.isfinite(xw[i]), fin)
+        assert_close(xw[i][fin], ref[fin], dtype)
+    for n in (1, 4, 33, 120):
+        a = rng.standard_normal((3, n, n)).astype(dtype) + 4 * np.eye(n, dtype=dtype)
+        bb = rng.standard_normal((3, n)).astype(dtype)
+        for lower in (False, True):
+            for unit in (False, True):
+                for trans in (False, True):
+                    x = host(_ops().triangular_solve(dev(a), dev(bb), lower, unit, trans))
+                    for i in range(3):
+                        xr = oracle.triangular_compute(a[i], bb[i], lower, unit, int(trans))
+                        assert_close(x[i], xr, dtype, factor=1e4)

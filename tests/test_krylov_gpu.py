@@ -1,0 +1,218 @@
+"""BiCGStab / GMRES / LSMR parity (GPU) vs the NumPy restatements of
+lineax/_solver/{bicgstab,gmres,lsmr}.py.  Tolerances per north_star."""
+import numpy as np
+import pytest
+
+import oracle
+from oracle import gen
+from tests.helpers import assert_close, dev, host
+
+pytestmark = pytest.mark.gpu
+MAXSTEPS_GIVEN, X64 = 4, 8
+
+
+def _ops():
+    from lineax_b200 import _ops
+
+    return _ops
+
+
+def _t(v):
+    return None if v is None else dev(v)
+
+
+def run_bicgstab(a, b, rtol, atol, max_steps=None, x64=None, precond=None, y0=None):
+    n = a.shape[-1]
+    ms = 10 * n if max_steps is None else max_steps
+    if x64 is None:
+        x64 = a.dtype == np.float64
+    flags = (0 if max_steps is None else MAXSTEPS_GIVEN) | (X64 if x64 else 0)
+    x, r, s = _ops().bicgstab(dev(a), dev(b), _t(precond), _t(y0), float(rtol), float(atol), ms, flags)
+    return host(x), host(r), host(s)
+
+
+def run_gmres(a, b, rtol, atol, max_steps=None, restart=20, stagnation_iters=20, precond=None, y0=None):
+    n = a.shape[-1]
+    ms = 10 * n if max_steps is None else max_steps
+    flags = 0 if max_steps is None else MAXSTEPS_GIVEN
+    x, r, s = _ops().gmres(dev(a), dev(b), _t(precond), _t(y0), float(rtol), float(atol), ms,
+                           min(restart, n), stagnation_iters, flags)
+    return host(x), host(r), host(s)
+
+
+def run_lsmr(a, b, rtol, atol, max_steps=None, conlim=1e8, y0=None):
+    m, n = a.shape[-2:]
+    if max_steps is None:
+        imax = np.iinfo(np.int32 if a.dtype == np.float32 else np.int64).max
+        ms = imax if min(m, n) > imax / 10 else 10 * min(m, n)
+    else:
+        ms = max_steps
+    flags = 0 if max_steps is None else MAXSTEPS_GIVEN
+    x, r, s, st = _ops().lsmr(dev(a), dev(b), _t(y0), float(rtol), float(atol), float(conlim), int(ms), flags)
+    return host(x), host(r), host(s), host(st)
+
+
+def batch_oracle(fn, a, b, *args, **kw):
+    per = {k: kw.pop(k) for k in ("preconditioner", "y0") if k in kw}
+    xs, rs, ss, sts = [], [], [], []
+    for i in range(a.shape[0]):
+        kwi = dict(kw)
+        for k, v in per.items():
+            kwi[k] = None if v is None else v[i]
+        x, r, st = fn(a[i], b[i], *args, **kwi)
+        xs.append(x), rs.append(r), ss.append(st["num_steps"]), sts.append(st)
+    return np.stack(xs), np.array(rs), np.array(ss), sts
+
+
+# ------------------------------------------------------------------ BiCGStab ----
+@pytest.mark.parametrize("n", [1, 3, 20, 64, 128, 256])
+@pytest.mark.parametrize("dtype,tol", [(np.float32, 1e-6), (np.float64, 1e-12)])
+def test_bicgstab_easy(n, dtype, tol):
+    a, b, _ = gen.easy_problem(10 + n, n, dtype, spd=False, batch=7)
+    x, res, steps = run_bicgstab(a, b, tol, tol)
+    xr, rr, sr, _ = batch_oracle(oracle.bicgstab, a, b, tol, tol)
+    assert np.all(np.abs(steps - sr) <= 2), (steps, sr)
+    same = steps == sr
+    # the signed fp32 breakdown test (bicgstab.py:110-113) is evaluated on the last iterate:
+    # require identical codes wherever the iteration counts agree
+    assert np.array_equal(res[same], rr[same]), (res, rr)
+    assert_close(x, xr, dtype, factor=20)
+
+
+def test_bicgstab_x64_flag_fp32_data():
+    a, b, _ = gen.easy_problem(5, 48, np.float32, spd=False, batch=5)
+    x, res, steps = run_bicgstab(a, b, 1e-6, 1e-6, x64=True)
+    xr, rr, sr, _ = batch_oracle(oracle.bicgstab, a, b, 1e-6, 1e-6, x64=True)
+    assert np.all(np.abs(steps - sr) <= 2) and np.array_equal(res, rr) and np.all(res == 0)
+    assert_close(x, xr, np.float32, factor=20)
+
+
+def test_bicgstab_max_steps_and_precond():
+    p = gen.poisson_matrix(100, np.float64)
+    rhs = np.random.default_rng(0).standard_normal(100)
+    x, res, steps = run_bicgstab(p[None], rhs[None], 0.0, 0.0, max_steps=2)
+    xr, rr, st = oracle.bicgstab(p, rhs, 0.0, 0.0, max_steps=2)
+    assert res[0] == rr == 0 and steps[0] == 2
+    assert_close(x[0], xr, np.float64, factor=1e3)
+    rng = np.random.default_rng(123)
+    A = rng.uniform(size=(10, 10)) + np.diag(np.arange(10.0) ** 6)
+    b = rng.uniform(size=10)
+    M = np.linalg.inv(A)
+    x, res, steps = run_bicgstab(A[None], b[None], 1e-12, 1e-12, max_steps=3, precond=M[None])
+    xr, rr, st = oracle.bicgstab(A, b, 1e-12, 1e-12, max_steps=3, preconditioner=M)
+    assert res[0] == rr and abs(int(steps[0]) - st["num_steps"]) <= 1
+    assert np.max(np.abs(x[0] - xr)) / np.abs(xr).max() < 1e-9
+
+
+# --------------------------------------------------------------------- GMRES ----
+@pytest.mark.parametrize("n", [1, 3, 20, 64, 128, 256, 300])
+@pytest.mark.parametrize("dtype,tol", [(np.float32, 1e-6), (np.float64, 1e-12)])
+def test_gmres_easy(n, dtype, tol):
+    a, b, _ = gen.easy_problem(20 + n, n, dtype, spd=False, batch=5)
+    x, res, steps = run_gmres(a, b, tol, tol)
+    xr, rr, sr, _ = batch_oracle(oracle.gmres, a, b, tol, tol)
+    assert np.all(np.abs(steps - sr) <= 2), (steps, sr)
+    assert np.array_equal(res, rr), (res, rr)
+    assert_close(x, xr, dtype, factor=20)
+
+
+def test_gmres_restart_100_gaussian():
+    """tests/test_solve.py:24-38."""
+    rng = np.random.default_rng(0)
+    a = rng.standard_normal((1, 100, 100))
+    xt = rng.standard_normal((1, 100))
+    b = np.einsum("bij,bj->bi", a, xt)
+    x, res, steps = run_gmres(a, b, 1e-10, 1e-10, restart=100)
+    xr, rr, st = oracle.gmres(a[0], b[0], 1e-10, 1e-10, restart=100)
+    assert res[0] == rr == 0 and abs(int(steps[0]) - st["num_steps"]) <= 2
+    assert np.max(np.abs(x[0] - xt[0])) < 1e-6
+
+
+def test_gmres_restart2_reports_failure():
+    """tests/test_singular.py:75-99: hard-coded 4x4, restart=2 must not be 'successful'."""
+    matrix = np.array([
+        [0.15892892, 0.05884365, -0.60427412, 0.1891916],
+        [-1.5484863, 0.93608822, 1.94888868, 1.37069667],
+        [0.62687318, -0.13996738, -0.6824359, 0.30975754],
+        [-0.67428635, 1.52372255, -0.88277754, 0.69633816],
+    ])
+    true_x = np.array([0.51383273, 1.72983427, -0.43251078, -1.11764668])
+    b = matrix @ true_x
+    x, res, steps = run_gmres(matrix[None], b[None], 1e-10, 1e-10, restart=2)
+    xr, rr, st = oracle.gmres(matrix, b, 1e-10, 1e-10, restart=2)
+    assert rr != 0 and res[0] == rr and abs(int(steps[0]) - st["num_steps"]) <= 2
+    rng = np.random.default_rng(0)
+    a = rng.standard_normal((100, 100))
+    bb = a @ rng.standard_normal(100)
+    x, res, steps = run_gmres(a[None], bb[None], 1e-10, 1e-10, restart=2)
+    xr, rr, st = oracle.gmres(a, bb, 1e-10, 1e-10, restart=2)
+    assert rr != 0 and res[0] != 0
+
+
+def test_gmres_max_steps_precond_y0():
+    p = gen.poisson_matrix(100, np.float64)
+    rhs = np.random.default_rng(0).standard_normal(100)
+    x, res, steps = run_gmres(p[None], rhs[None], 0.0, 0.0, max_steps=2)
+    xr, rr, st = oracle.gmres(p, rhs, 0.0, 0.0, max_steps=2)
+    assert res[0] == rr == 0 and steps[0] == st["num_steps"] == 2
+    assert_close(x[0], xr, np.float64, factor=1e4)
+    rng = np.random.default_rng(123)
+    A = rng.uniform(size=(10, 10)) + np.diag(np.arange(10.0) ** 6)
+    b = rng.uniform(size=10)
+    M = np.linalg.inv(A)
+    x, res, steps = run_gmres(A[None], b[None], 1e-12, 1e-12, max_steps=4, restart=1, precond=M[None])
+    xr, rr, st = oracle.gmres(A, b, 1e-12, 1e-12, max_steps=4, restart=1, preconditioner=M)
+    assert res[0] == rr and abs(int(steps[0]) - st["num_steps"]) <= 1
+    # exact solution as y0: immediate convergence path (initial breakdown handling)
+    a, b, xt = gen.easy_problem(4, 30, np.float64, spd=False)
+    x, res, steps = run_gmres(a[None], b[None], 1e-8, 1e-8, y0=np.linalg.solve(a, b)[None])
+    xr, rr, st = oracle.gmres(a, b, 1e-8, 1e-8, y0=np.linalg.solve(a, b))
+    assert res[0] == rr and abs(int(steps[0]) - st["num_steps"]) <= 1
+
+
+# ---------------------------------------------------------------------- LSMR ----
+@pytest.mark.parametrize("shape", [(1, 1), (5, 3), (3, 5), (64, 64), (300, 40), (40, 300), (1024, 64)])
+@pytest.mark.parametrize("dtype,tol", [(np.float32, 1e-6), (np.float64, 1e-12)])
+def test_lsmr_vs_oracle(shape, dtype, tol):
+    m, n = shape
+    rng = np.random.default_rng(m * 1000 + n)
+    a = (rng.standard_normal((4, m, n)) / np.sqrt(max(m, n))).astype(dtype)
+    b = rng.standard_normal((4, m)).astype(dtype)
+    x, res, steps, st = run_lsmr(a, b, tol, tol)
+    xr, rr, sr, sts = batch_oracle(oracle.lsmr, a, b, tol, tol)
+    assert np.all(np.abs(steps - sr) <= 2), (steps, sr)
+    assert np.array_equal(res, rr)
+    assert_close(x, xr, dtype, factor=200)
+    same = steps == sr
+    for i in np.nonzero(same)[0]:
+        assert int(st[i, 0]) == sts[i]["istop"]
+        for j, key in enumerate(["norm_r", "norm_Ar", "norm_A", "cond_A", "norm_x"]):
+            ref = float(sts[i][key])
+            assert abs(float(st[i, 1 + j]) - ref) <= 1e-3 * abs(ref) + 1e-5 * max(1.0, float(sts[i]["norm_r"]))
+
+
+def test_lsmr_diag_cases():
+    """tests/test_lsmr.py:7-30: conlim on diag(1e8..1), exact zeros for zero / null-space rhs."""
+    ill = np.diag([1e8, 1e6, 1e4, 1e2, 1.0])
+    well = np.diag([2.0, 4.0, 5.0, 8.0, 10.0])
+    sing = np.diag([0.0, 4.0, 5.0, 8.0, 10.0])
+    x, res, steps, st = run_lsmr(ill[None], np.ones((1, 5)), 1e-10, 1e-10)
+    xr, rr, s = oracle.lsmr(ill, np.ones(5), 1e-10, 1e-10)
+    assert rr == oracle.RESULTS.conlim and res[0] == rr
+    for mat in (ill, well, sing):
+        x, res, steps, st = run_lsmr(mat[None], np.zeros((1, 5)), 1e-10, 1e-10)
+        assert np.all(x == 0) and res[0] == 0
+    e0 = np.zeros((1, 5))
+    e0[0, 0] = 1.0
+    x, res, steps, st = run_lsmr(sing[None], e0, 1e-10, 1e-10)
+    assert np.all(x == 0) and res[0] == 0
+
+
+def test_lsmr_c5_shape_reduced():
+    """C5-LSMR generator at reduced size (16384 x 256): istop and iteration count."""
+    a, b, _ = gen.tall_lstsq(3, 16384, 256, np.float32)
+    x, res, steps, st = run_lsmr(a[None], b[None], 1e-6, 1e-6)
+    xr, rr, s = oracle.lsmr(a, b, 1e-6, 1e-6)
+    assert res[0] == rr == 0 and abs(int(steps[0]) - s["num_steps"]) <= 2
+    xl = np.linalg.lstsq(a.astype(np.float64), b.astype(np.float64), rcond=None)[0]
+    assert np.max(np.abs(x[0] - xl)) / np.abs(xl).max() < 1e-4
