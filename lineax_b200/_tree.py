@@ -65,6 +65,10 @@ def inexact_asarray(x, device=None) -> torch.Tensor:
     """lineax/_misc.py:82-86: arrays of inexact dtype; other leaves promoted to the default float."""
     if isinstance(x, torch.Tensor):
         t = x
+        if not t.is_cuda and device is None and default_device().type == "cuda":
+            t = t.to(default_device())  # host arrays are accepted and staged to the GPU
+        elif device is not None and t.device != torch.device(device):
+            t = t.to(device)
     else:
         import numpy as np
 
