@@ -57,8 +57,8 @@ def _check_cuda(*ts):
             )
 
 
-def _define(name: str, fn, *, n_out: int):
-    op = torch.library.custom_op(f"lineax_b200::{name}", fn, mutates_args=(), device_types="cuda")
+def _define(name: str, fn, *, n_out: int, device_types="cuda"):
+    op = torch.library.custom_op(f"lineax_b200::{name}", fn, mutates_args=(), device_types=device_types)
 
     def rule(info, in_dims, *args):
         new = []
@@ -200,7 +200,7 @@ def _throw_if_failed(result: Tensor) -> Tensor:
     return result.clone()
 
 
-throw_if_failed = _define("throw_if_failed", _throw_if_failed, n_out=1)
+throw_if_failed = _define("throw_if_failed", _throw_if_failed, n_out=1, device_types=None)  # host logic only
 
 
 # ------------------------------------------------------ operator application ----

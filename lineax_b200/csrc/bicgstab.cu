@@ -135,7 +135,8 @@ int bicgstab_dispatch(KrylovParams<T> p, cudaStream_t st) {
   int occ = 1;
   LXB_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kKrylovThreads, smem));
   if (occ < 1) occ = 1;
-  const int64_t cap = (int64_t)kNumSMs * occ;
+  int64_t cap = (int64_t)kNumSMs * occ;
+  if (!p.a_smem) cap = l2_resident_cap(cap, mat_bytes);
   const int64_t blocks = p.batch < cap ? p.batch : cap;
   kern<<<(unsigned)blocks, kKrylovThreads, smem, st>>>(p);
   LXB_CUDA_CHECK_LAUNCH();

@@ -255,7 +255,8 @@ int gmres_dispatch(KrylovParams<T> p, void* ws, size_t ws_bytes, cudaStream_t st
   int occ = 1;
   LXB_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kKrylovThreads, pl.smem));
   if (occ < 1) occ = 1;
-  const int64_t cap = (int64_t)kNumSMs * occ;
+  int64_t cap = (int64_t)kNumSMs * occ;
+  if (!p.a_smem) cap = l2_resident_cap(cap, pl.mat_bytes);
   const int64_t blocks = p.batch < cap ? p.batch : cap;
   if (pl.basis_smem) {
     p.ws = nullptr;

@@ -2,6 +2,8 @@
 // The system's vectors live in shared memory for the whole solve; A is either staged into
 // shared memory once per solve (A_SMEM) or streamed from global/L2 on every matvec.
 #pragma once
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace lxb {
@@ -69,17 +71,47 @@ __device__ __forceinline__ T row_dot(const T* __restrict__ row, const T* __restr
 }
 
 // y[0:m] = scale * (A[m,n] @ x[0:n]); A row-major with leading dimension lda.
+// Each warp takes 4 rows at a time so that every lane keeps >= 8 independent 128-bit loads in
+// flight (A streams from HBM/L2 or shared memory); x is read once per 4 rows.
 // Ends with __syncthreads().
 template <typename T>
 __device__ __forceinline__ void cta_matvec(const T* __restrict__ A, int lda, int m, int n,
                                            const T* __restrict__ x, T* __restrict__ y, T scale) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
   constexpr int V = 16 / sizeof(T);
+  constexpr int RB = 4;
   const bool vec = (n % V == 0) && (lda % V == 0) && ((reinterpret_cast<uintptr_t>(A) & 15) == 0);
   if (vec) {
-    for (int i = warp; i < m; i += nw) {
-      const T s = row_dot<T, true>(A + (size_t)i * lda, x, n, lane);
-      if (lane == 0) y[i] = scale * s;
+    using VT = typename V16K<T>::type;
+    const VT* x4 = reinterpret_cast<const VT*>(x);
+    const int nv = n / V;
+    for (int i0 = warp * RB; i0 < m; i0 += nw * RB) {
+      T acc[RB];
+      const VT* rows[RB];
+#pragma unroll
+      for (int r = 0; r < RB; ++r) {
+        acc[r] = T(0);
+        const int i = i0 + r < m ? i0 + r : m - 1;  // clamp: duplicates are discarded below
+        rows[r] = reinterpret_cast<const VT*>(A + (size_t)i * lda);
+      }
+      for (int c = lane; c < nv; c += 32) {
+        VT a[RB];
+#pragma unroll
+        for (int r = 0; r < RB; ++r) a[r] = rows[r][c];
+        const VT b = x4[c];
+        const T* pb = reinterpret_cast<const T*>(&b);
+#pragma unroll
+        for (int r = 0; r < RB; ++r) {
+          const T* pa = reinterpret_cast<const T*>(&a[r]);
+#pragma unroll
+          for (int e = 0; e < V; ++e) acc[r] = fma_(pa[e], pb[e], acc[r]);
+        }
+      }
+#pragma unroll
+      for (int r = 0; r < RB; ++r) {
+        const T s = warp_sum(acc[r]);
+        if (lane == 0 && i0 + r < m) y[i0 + r] = scale * s;
+      }
     }
   } else {
     for (int i = warp; i < m; i += nw) {
@@ -150,6 +182,21 @@ __device__ __forceinline__ bool cta_not_converged(const T* r, const T* diff, con
   }
   block_absmax<T, 2>(v, red);
   return (v[0] > T(1)) || (v[1] > T(1));
+}
+
+// When A is streamed on every matvec, limit the number of co-resident systems so that their
+// matrices together stay inside the 126 MB L2 (re-reads then hit L2 instead of HBM), but never
+// below one CTA per SM.
+inline int64_t l2_resident_cap(int64_t cap, size_t mat_bytes) {
+  // experiment knob (MB of L2 to budget); 0/unset = no cap.  Measured on B200 (cg256): with
+  // the cap the kernel is L2-latency bound and slower than streaming from HBM at full occupancy.
+  const char* env = getenv("LXB_L2_CAP_MB");
+  const size_t mb = env ? (size_t)atol(env) : 0;
+  if (mb == 0) return cap;
+  const size_t budget = mb << 20;
+  int64_t fit = mat_bytes ? (int64_t)(budget / mat_bytes) : cap;
+  if (fit < kNumSMs) fit = kNumSMs;
+  return cap < fit ? cap : fit;
 }
 
 // cg.py:213-222 (shared by every iterative solver)

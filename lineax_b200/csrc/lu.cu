@@ -95,20 +95,24 @@ __device__ __forceinline__ int pick_pivot(double v, bool cand, int pos) {
 // Elimination on a register-resident system. On exit lane r holds (in LAPACK's final
 // layout) row `pos` of the packed LU factors, `bb` the forward-substituted right-hand side
 // for that row, `rdiag` = 1/u_pos,pos and `mypiv` = piv[lane].
-template <typename T, int NP, bool SOLVE>
+template <typename T, int NP, bool SOLVE, bool FULL>
 __device__ __forceinline__ void lu_eliminate(T (&a)[NP], T& bb, int& pos, T& rdiag, int& mypiv,
                                              T* urow, int lane, int n) {
   using VT = typename V16<T>::type;
   constexpr int V = 16 / sizeof(T);
   constexpr int CPR = NP / V;
-  const bool real = lane < NP;
+  const bool real = NP == 32 || lane < NP;
   pos = lane;
   rdiag = T(0);
   mypiv = lane;
 #pragma unroll
   for (int k = 0; k < NP; ++k) {
-    if (k < n) {
+    if (FULL || k < n) {
+      // every lane inverts its own candidate while the pivot search is in flight; the pivot
+      // lane's value is the 1/pivot everybody needs (same IEEE division, shorter critical path)
+      const T rown = T(1) / a[k];
       const int pl = pick_pivot(a[k], real && pos >= k, pos);
+      const T r = __shfl_sync(kFull, rown, pl);
       const int ppos = __shfl_sync(kFull, pos, pl);
       if (lane == k) mypiv = ppos;
       if (pos == k) pos = ppos;
@@ -135,7 +139,6 @@ __device__ __forceinline__ void lu_eliminate(T (&a)[NP], T& bb, int& pos, T& rdi
 #pragma unroll
         for (int e = 0; e < V; ++e) u[c * V + e] = pv[e];
       }
-      const T r = T(1) / u[k];
       if (lane == pl) rdiag = r;
       if (real && pos > k) {
         const T l = a[k] * r;
@@ -149,13 +152,13 @@ __device__ __forceinline__ void lu_eliminate(T (&a)[NP], T& bb, int& pos, T& rdi
 }
 
 // Back substitution U x = y on the register-resident factors (rows addressed by `pos`).
-template <typename T, int NP>
+template <typename T, int NP, bool FULL>
 __device__ __forceinline__ T lu_backsolve(const T (&a)[NP], T bb, int pos, T rdiag, int lane,
                                           int n) {
   T mine = T(0);
 #pragma unroll
   for (int k = NP - 1; k >= 0; --k) {
-    if (k < n) {
+    if (FULL || k < n) {
       const int pl = __ffs(__ballot_sync(kFull, pos == k)) - 1;
       const T xk = __shfl_sync(kFull, bb * rdiag, pl);
       if (pos < k) bb = fma_(-a[k], xk, bb);
@@ -166,8 +169,8 @@ __device__ __forceinline__ T lu_backsolve(const T (&a)[NP], T bb, int pos, T rdi
 }
 
 // MODE: 0 = factor only, 1 = factor + solve (lu/piv optional)
-template <typename T, int NP, bool SOLVE>
-__global__ void __launch_bounds__(kLuWarps * 32)
+template <typename T, int NP, bool SOLVE, bool FULL>
+__global__ void __launch_bounds__(kLuWarps * 32, (sizeof(T) == 4 && NP == 32) ? 3 : 1)
     lu_warp_kernel(const T* __restrict__ A, int64_t sA, const T* __restrict__ B, int64_t sB,
                    T* __restrict__ X, T* __restrict__ LU, int32_t* __restrict__ PIV, int64_t batch,
                    int n, int fast) {
@@ -197,7 +200,7 @@ __global__ void __launch_bounds__(kLuWarps * 32)
     if (SOLVE && lane < n) bb = B[sys * sB + lane];
     int pos, mypiv;
     T rdiag;
-    lu_eliminate<T, NP, SOLVE>(a, bb, pos, rdiag, mypiv, urow, lane, n);
+    lu_eliminate<T, NP, SOLVE, FULL>(a, bb, pos, rdiag, mypiv, urow, lane, n);
     if (LU != nullptr && lane < NP && pos < n) {
       T* dst = LU + sys * (int64_t)n * n + (size_t)pos * n;
       if (fast) {
@@ -219,7 +222,7 @@ __global__ void __launch_bounds__(kLuWarps * 32)
     }
     if (PIV != nullptr && lane < n) PIV[sys * n + lane] = mypiv;
     if (SOLVE) {
-      const T xm = lu_backsolve<T, NP>(a, bb, pos, rdiag, lane, n);
+      const T xm = lu_backsolve<T, NP, FULL>(a, bb, pos, rdiag, lane, n);
       if (lane < n) X[sys * n + lane] = xm;
     }
   }
@@ -508,11 +511,11 @@ __global__ void __launch_bounds__(kLuBlockThreads)
 // ------------------------------------------------------------ launchers ----
 constexpr size_t kMaxSmem = 227 * 1024;
 
-template <typename T, int NP, bool SOLVE>
-int launch_lu_warp(const T* A, int64_t sA, const T* b, int64_t sb, T* x, T* lu, int32_t* piv,
-                   int64_t batch, int n, cudaStream_t st) {
+template <typename T, int NP, bool SOLVE, bool FULL>
+int launch_lu_warp_impl(const T* A, int64_t sA, const T* b, int64_t sb, T* x, T* lu, int32_t* piv,
+                        int64_t batch, int n, cudaStream_t st) {
   const size_t smem = (size_t)kLuWarps * (NP * NP + 2 * NP) * sizeof(T);
-  auto kern = lu_warp_kernel<T, NP, SOLVE>;
+  auto kern = lu_warp_kernel<T, NP, SOLVE, FULL>;
   LXB_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int fast = (n == NP) && aligned16(A) && ((sA * sizeof(T)) % 16 == 0) &&
                    (lu == nullptr || aligned16(lu));
@@ -525,6 +528,13 @@ int launch_lu_warp(const T* A, int64_t sA, const T* b, int64_t sb, T* x, T* lu, 
   kern<<<(unsigned)blocks, kLuWarps * 32, smem, st>>>(A, sA, b, sb, x, lu, piv, batch, n, fast);
   LXB_CUDA_CHECK_LAUNCH();
   return 0;
+}
+
+template <typename T, int NP, bool SOLVE>
+int launch_lu_warp(const T* A, int64_t sA, const T* b, int64_t sb, T* x, T* lu, int32_t* piv,
+                   int64_t batch, int n, cudaStream_t st) {
+  if (n == NP) return launch_lu_warp_impl<T, NP, SOLVE, true>(A, sA, b, sb, x, lu, piv, batch, n, st);
+  return launch_lu_warp_impl<T, NP, SOLVE, false>(A, sA, b, sb, x, lu, piv, batch, n, st);
 }
 
 template <typename T, bool SOLVE>
