@@ -48,6 +48,13 @@ def _ptr(t: Optional[Tensor]):
     return None if t is None else t.data_ptr()
 
 
+def _workspace(name: str, device, *args):
+    nbytes = nat.fn(name)(*args)
+    if not nbytes:
+        return None, 0
+    return torch.empty(nbytes, dtype=torch.uint8, device=device), nbytes
+
+
 def _check_cuda(*ts):
     for t in ts:
         if t is not None and not t.is_cuda:
@@ -159,9 +166,10 @@ def _cg(a: Tensor, b: Tensor, precond: Optional[Tensor], y0: Optional[Tensor], r
             x = torch.empty(full + (n,), dtype=a.dtype, device=a.device)
         result = torch.empty(full, dtype=torch.int32, device=a.device)
         steps = torch.empty(full, dtype=torch.int32, device=a.device)
+        ws, ws_bytes = _workspace(f"lxb_cg_workspace_{sfx}", a.device, B, n)
         nat.call(f"lxb_cg_{sfx}", a_.data_ptr(), s_a, b_.data_ptr(), s_b, _ptr(m_), s_m, x.data_ptr(),
                  result.data_ptr(), steps.data_ptr(), B, n, rtol, atol, max_steps, stabilise_every,
-                 flags, None, 0, _stream())
+                 flags, _ptr(ws), ws_bytes, _stream())
     return x, result, steps
 
 
@@ -323,9 +331,10 @@ def _bicgstab(a: Tensor, b: Tensor, precond: Optional[Tensor], y0: Optional[Tens
             x = torch.empty(full + (n,), dtype=a.dtype, device=a.device)
         result = torch.empty(full, dtype=torch.int32, device=a.device)
         steps = torch.empty(full, dtype=torch.int32, device=a.device)
+        ws, ws_bytes = _workspace(f"lxb_bicgstab_workspace_{sfx}", a.device, B, n)
         nat.call(f"lxb_bicgstab_{sfx}", a_.data_ptr(), s_a, b_.data_ptr(), s_b, _ptr(m_), s_m,
                  x.data_ptr(), result.data_ptr(), steps.data_ptr(), B, n, rtol, atol, max_steps, flags,
-                 None, 0, _stream())
+                 _ptr(ws), ws_bytes, _stream())
     return x, result, steps
 
 
@@ -377,9 +386,10 @@ def _lsmr(a: Tensor, b: Tensor, y0: Optional[Tensor], rtol: float, atol: float, 
         result = torch.empty(full, dtype=torch.int32, device=a.device)
         steps = torch.empty(full, dtype=torch.int32, device=a.device)
         stats = torch.empty(full + (8,), dtype=a.dtype, device=a.device)
+        ws, ws_bytes = _workspace(f"lxb_lsmr_workspace_{sfx}", a.device, B, m, n)
         nat.call(f"lxb_lsmr_{sfx}", a_.data_ptr(), s_a, b_.data_ptr(), s_b, x.data_ptr(),
                  result.data_ptr(), steps.data_ptr(), stats.data_ptr(), B, m, n, rtol, atol, conlim,
-                 max_steps, flags, None, 0, _stream())
+                 max_steps, flags, _ptr(ws), ws_bytes, _stream())
     return x, result, steps, stats
 
 

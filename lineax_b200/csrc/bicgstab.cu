@@ -2,6 +2,7 @@
 // (one CTA per system; two matvecs, five dots, the axpys and the breakdown / convergence
 // tests per iteration, no host round trips).
 #include "krylov_cta.cuh"
+#include "krylov_grid_api.cuh"
 
 namespace lxb {
 
@@ -120,13 +121,13 @@ __global__ void __launch_bounds__(kKrylovThreads) bicgstab_cta_kernel(KrylovPara
 }
 
 template <typename T>
-int bicgstab_dispatch(KrylovParams<T> p, cudaStream_t st) {
+int bicgstab_dispatch(KrylovParams<T> p, void* ws, size_t ws_bytes, cudaStream_t st) {
   if (p.batch < 0 || p.n < 0 || !p.A || !p.b || !p.x || !p.result || !p.num_steps) return LXB_E_BADARG;
   if (p.batch == 0) return 0;
   const size_t kMax = 227 * 1024;
   const size_t npad = ((size_t)p.n + 3) & ~(size_t)3;
   const size_t vec_bytes = (11 * npad + 96) * sizeof(T);
-  if (vec_bytes > kMax) return LXB_E_UNSUPPORTED;
+  if (use_grid_tier(p.batch, p.n, p.n) || vec_bytes > kMax) return bicgstab_grid_launch<T>(p, ws, ws_bytes, st);
   const size_t mat_bytes = (size_t)p.n * p.n * sizeof(T);
   p.a_smem = (vec_bytes + mat_bytes <= kMax) && p.n > 0;
   const size_t smem = vec_bytes + (p.a_smem ? mat_bytes : 0);
@@ -151,18 +152,15 @@ int bicgstab_dispatch(KrylovParams<T> p, cudaStream_t st) {
                                     int32_t* num_steps, int64_t batch, int32_t n, T rtol, T atol,  \
                                     int32_t max_steps, int32_t flags, void* workspace,             \
                                     size_t workspace_bytes, lxb_stream_t stream) {                 \
-    (void)workspace;                                                                               \
-    (void)workspace_bytes;                                                                         \
     lxb::KrylovParams<T> p{};                                                                      \
     p.A = A; p.sA = stride_A; p.b = b; p.sb = stride_b; p.M = Minv; p.sM = stride_M; p.x = x;      \
     p.result = result; p.num_steps = num_steps; p.batch = batch; p.m = n; p.n = n;                 \
     p.rtol = rtol; p.atol = atol; p.max_steps = max_steps; p.flags = flags;                        \
-    return lxb::bicgstab_dispatch<T>(p, (cudaStream_t)stream);                                     \
+    return lxb::bicgstab_dispatch<T>(p, workspace, workspace_bytes, (cudaStream_t)stream);                                     \
   }                                                                                                \
   extern "C" size_t lxb_bicgstab_workspace_##sfx(int64_t batch, int32_t n) {                       \
-    (void)batch;                                                                                   \
-    (void)n;                                                                                       \
-    return 0;                                                                                      \
+    const bool big = (11 * (((size_t)n + 3) & ~(size_t)3) + 96) * sizeof(T) > 227 * 1024;          \
+    return (lxb::use_grid_tier(batch, n, n) || big) ? lxb::bicgstab_grid_ws_bytes<T>(n) : 0;       \
   }
 LXB_DEF_BICGSTAB(f32, float)
 LXB_DEF_BICGSTAB(f64, double)

@@ -4,6 +4,7 @@
 // as soon as its own test passes (observably equal to JAX's masked lock-step loop,
 // SURVEY.md App. B-3).
 #include "krylov_cta.cuh"
+#include "krylov_grid_api.cuh"
 
 namespace lxb {
 
@@ -109,12 +110,12 @@ __global__ void __launch_bounds__(kKrylovThreads) cg_cta_kernel(KrylovParams<T> 
 constexpr size_t kMaxSmemK = 227 * 1024;
 
 template <typename T>
-int cg_dispatch(KrylovParams<T> p, cudaStream_t st) {
+int cg_dispatch(KrylovParams<T> p, void* ws, size_t ws_bytes, cudaStream_t st) {
   if (p.batch < 0 || p.n < 0 || !p.A || !p.b || !p.x || !p.result || !p.num_steps) return LXB_E_BADARG;
   if (p.batch == 0) return 0;
   const size_t npad = ((size_t)p.n + 3) & ~(size_t)3;
   const size_t vec_bytes = (6 * npad + 96) * sizeof(T);
-  if (vec_bytes > kMaxSmemK) return LXB_E_UNSUPPORTED;
+  if (use_grid_tier(p.batch, p.n, p.n) || vec_bytes > kMaxSmemK) return cg_grid_launch<T>(p, ws, ws_bytes, st);
   const size_t mat_bytes = (size_t)p.n * p.n * sizeof(T);
   p.a_smem = (vec_bytes + mat_bytes <= kMaxSmemK) && p.n > 0;
   const size_t smem = vec_bytes + (p.a_smem ? mat_bytes : 0);
@@ -139,19 +140,16 @@ int cg_dispatch(KrylovParams<T> p, cudaStream_t st) {
                               int32_t* num_steps, int64_t batch, int32_t n, T rtol, T atol,        \
                               int32_t max_steps, int32_t stabilise_every, int32_t flags,           \
                               void* workspace, size_t workspace_bytes, lxb_stream_t stream) {      \
-    (void)workspace;                                                                               \
-    (void)workspace_bytes;                                                                         \
     lxb::KrylovParams<T> p{};                                                                      \
     p.A = A; p.sA = stride_A; p.b = b; p.sb = stride_b; p.M = Minv; p.sM = stride_M; p.x = x;      \
     p.result = result; p.num_steps = num_steps; p.batch = batch; p.m = n; p.n = n;                 \
     p.rtol = rtol; p.atol = atol; p.max_steps = max_steps; p.stabilise_every = stabilise_every;    \
     p.flags = flags;                                                                               \
-    return lxb::cg_dispatch<T>(p, (cudaStream_t)stream);                                           \
+    return lxb::cg_dispatch<T>(p, workspace, workspace_bytes, (cudaStream_t)stream);                                           \
   }                                                                                                \
   extern "C" size_t lxb_cg_workspace_##sfx(int64_t batch, int32_t n) {                             \
-    (void)batch;                                                                                   \
-    (void)n;                                                                                       \
-    return 0;                                                                                      \
+    const bool big = (6 * (((size_t)n + 3) & ~(size_t)3) + 96) * sizeof(T) > lxb::kMaxSmemK;       \
+    return (lxb::use_grid_tier(batch, n, n) || big) ? lxb::cg_grid_ws_bytes<T>(n) : 0;             \
   }
 LXB_DEF_CG(f32, float)
 LXB_DEF_CG(f64, double)

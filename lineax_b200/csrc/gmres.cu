@@ -8,6 +8,7 @@
 // The Krylov basis lives in shared memory when it fits, otherwise in the caller's workspace
 // (L2-resident for the sizes of interest).
 #include "krylov_cta.cuh"
+#include "krylov_grid_api.cuh"
 
 namespace lxb {
 
@@ -241,6 +242,13 @@ GmresPlan<T> gmres_plan(int n, int R) {
 }
 
 template <typename T>
+bool gmres_wants_grid(int64_t batch, int n, int restart) {
+  if (restart > n) restart = n;
+  if (restart + 2 > kGridMaxKHost) return false;
+  return use_grid_tier(batch, n, n) || gmres_plan<T>(n, restart).fixed_bytes > 227 * 1024;
+}
+
+template <typename T>
 int gmres_dispatch(KrylovParams<T> p, void* ws, size_t ws_bytes, cudaStream_t st) {
   if (p.batch < 0 || p.n < 0 || p.restart < 0 || !p.A || !p.b || !p.x || !p.result || !p.num_steps)
     return LXB_E_BADARG;
@@ -248,6 +256,7 @@ int gmres_dispatch(KrylovParams<T> p, void* ws, size_t ws_bytes, cudaStream_t st
   if (p.restart > p.n) p.restart = p.n;  // gmres.py:128
   if (p.n == 0) p.restart = 0;
   const GmresPlan<T> pl = gmres_plan<T>(p.n, p.restart);
+  if (gmres_wants_grid<T>(p.batch, p.n, p.restart)) return gmres_grid_launch<T>(p, ws, ws_bytes, st);
   if (pl.fixed_bytes > 227 * 1024) return LXB_E_UNSUPPORTED;
   p.a_smem = pl.a_smem;
   auto kern = gmres_cta_kernel<T>;
@@ -290,6 +299,7 @@ int gmres_dispatch(KrylovParams<T> p, void* ws, size_t ws_bytes, cudaStream_t st
   extern "C" size_t lxb_gmres_workspace_##sfx(int64_t batch, int32_t n, int32_t restart) {         \
     if (batch <= 0 || n <= 0) return 0;                                                            \
     if (restart > n) restart = n;                                                                  \
+    if (lxb::gmres_wants_grid<T>(batch, n, restart)) return lxb::gmres_grid_ws_bytes<T>(n, restart); \
     const lxb::GmresPlan<T> pl = lxb::gmres_plan<T>(n, restart);                                   \
     if (pl.basis_smem) return 0;                                                                   \
     const int64_t cap = (int64_t)lxb::kNumSMs * 8;                                                 \

@@ -1,0 +1,200 @@
+// "Whole grid per system" tier of the Krylov kernels: one persistent COOPERATIVE kernel in which
+// every CTA owns a contiguous block of rows of A and the matching slice of every vector.
+// Vectors live in global memory (L2-resident), the matvec streams A once from HBM with 128-bit
+// non-L1-allocating loads, dot products / norms are reduced through a per-CTA partial array and
+// one grid barrier (deterministic order, no atomics), and the whole iteration -- including the
+// convergence / breakdown tests -- stays on the device.
+#pragma once
+#include <cooperative_groups.h>
+
+#include "krylov_cta.cuh"
+
+namespace lxb {
+
+namespace cgx = cooperative_groups;
+
+constexpr int kGridThreads = 256;
+constexpr int kGridMaxK = 40;  // widest reduction (GMRES restart + 1 <= 40 in grid mode)
+
+template <typename T>
+struct GridTeam {
+  cgx::grid_group g;
+  int nb, bid, tid, nt;
+  T* part;  // global scratch: 2 x kGridMaxK x nb
+  int flip;
+  T* red;   // shared scratch, >= 96 + kGridMaxK elements
+
+  __device__ GridTeam(T* part_, T* red_)
+      : g(cgx::this_grid()), nb(gridDim.x), bid(blockIdx.x), tid(threadIdx.x), nt(blockDim.x),
+        part(part_), flip(0), red(red_) {}
+
+  __device__ __forceinline__ void sync() { g.sync(); }
+
+  // contiguous slice [lo, hi) of `n` items owned by this CTA (multiples of 4 where possible)
+  __device__ __forceinline__ void slice(int n, int& lo, int& hi) const {
+    const int per = (((n + nb - 1) / nb) + 3) & ~3;
+    lo = bid * per < n ? bid * per : n;
+    hi = lo + per < n ? lo + per : n;
+  }
+
+  // All-reduce KS sums and KM NaN-propagating abs-maxima of per-thread values. Every thread of
+  // every CTA returns the same bits. Contains exactly one grid barrier.
+  template <int KS, int KM>
+  __device__ void reduce(T* s, T* m) {
+    if (KS > 0) {
+      T tmp[KS > 0 ? KS : 1];
+      for (int k = 0; k < KS; ++k) tmp[k] = s[k];
+      block_sum<T, (KS > 0 ? KS : 1)>(tmp, red);
+      for (int k = 0; k < KS; ++k) s[k] = tmp[k];
+    }
+    if (KM > 0) {
+      T tmp[KM > 0 ? KM : 1];
+      for (int k = 0; k < KM; ++k) tmp[k] = m[k];
+      block_absmax<T, (KM > 0 ? KM : 1)>(tmp, red);
+      for (int k = 0; k < KM; ++k) m[k] = tmp[k];
+    }
+    T* buf = part + (size_t)flip * kGridMaxK * nb;
+    flip ^= 1;
+    if (tid == 0) {
+      for (int k = 0; k < KS; ++k) buf[(size_t)k * nb + bid] = s[k];
+      for (int k = 0; k < KM; ++k) buf[(size_t)(KS + k) * nb + bid] = m[k];
+      __threadfence();
+    }
+    g.sync();
+    for (int k = 0; k < KS; ++k) {
+      T a[1] = {T(0)};
+      for (int i = tid; i < nb; i += nt) a[0] += __ldcg(buf + (size_t)k * nb + i);
+      block_sum<T, 1>(a, red);
+      s[k] = a[0];
+    }
+    for (int k = 0; k < KM; ++k) {
+      T a[1] = {T(0)};
+      for (int i = tid; i < nb; i += nt) a[0] = absmax2(a[0], __ldcg(buf + (size_t)(KS + k) * nb + i));
+      block_absmax<T, 1>(a, red);
+      m[k] = a[0];
+    }
+  }
+
+  // Runtime-K sum all-reduce: `vals` (shared memory, K <= kGridMaxK entries, already reduced
+  // within the CTA and visible to all its threads) -> global sums written back to `vals`.
+  __device__ void reduce_dyn(T* vals, int K) {
+    T* buf = part + (size_t)flip * kGridMaxK * nb;
+    flip ^= 1;
+    __syncthreads();
+    for (int k = tid; k < K; k += nt) buf[(size_t)k * nb + bid] = vals[k];
+    __threadfence();
+    g.sync();
+    const int lane = tid & 31, warp = tid >> 5, nw = nt >> 5;
+    for (int k = warp; k < K; k += nw) {
+      T a = T(0);
+      for (int i = lane; i < nb; i += 32) a += __ldcg(buf + (size_t)k * nb + i);
+      a = warp_sum(a);
+      if (lane == 0) vals[k] = a;
+    }
+    __syncthreads();
+  }
+};
+
+// y[lo:hi) = scale * A[lo:hi, :] x, A streamed (no L1 allocation), x through L1/L2.
+// Ends with __syncthreads().
+template <typename T>
+__device__ __forceinline__ void grid_matvec(const T* __restrict__ A, int n, int lo, int hi,
+                                            const T* __restrict__ x, T* __restrict__ y, T scale) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  constexpr int V = 16 / sizeof(T);
+  constexpr int RB = 4;
+  using VT = typename V16K<T>::type;
+  const bool vec = (n % V == 0) && ((reinterpret_cast<uintptr_t>(A) & 15) == 0) &&
+                   ((reinterpret_cast<uintptr_t>(x) & 15) == 0);
+  if (vec) {
+    const VT* x4 = reinterpret_cast<const VT*>(x);
+    const int nv = n / V;
+    for (int i0 = lo + warp * RB; i0 < hi; i0 += nw * RB) {
+      T acc[RB];
+      const VT* rows[RB];
+#pragma unroll
+      for (int r = 0; r < RB; ++r) {
+        acc[r] = T(0);
+        const int i = i0 + r < hi ? i0 + r : hi - 1;
+        rows[r] = reinterpret_cast<const VT*>(A + (size_t)i * n);
+      }
+#pragma unroll 2
+      for (int c = lane; c < nv; c += 32) {
+        VT a[RB];
+#pragma unroll
+        for (int r = 0; r < RB; ++r) a[r] = ldg_stream(rows[r] + c);
+        const VT b = x4[c];
+        const T* pb = reinterpret_cast<const T*>(&b);
+#pragma unroll
+        for (int r = 0; r < RB; ++r) {
+          const T* pa = reinterpret_cast<const T*>(&a[r]);
+#pragma unroll
+          for (int e = 0; e < V; ++e) acc[r] = fma_(pa[e], pb[e], acc[r]);
+        }
+      }
+#pragma unroll
+      for (int r = 0; r < RB; ++r) {
+        const T s = warp_sum(acc[r]);
+        if (lane == 0 && i0 + r < hi) y[i0 + r] = scale * s;
+      }
+    }
+  } else {
+    for (int i = lo + warp; i < hi; i += nw) {
+      const T s = row_dot<T, false>(A + (size_t)i * n, x, n, lane);
+      if (lane == 0) y[i] = scale * s;
+    }
+  }
+  __syncthreads();  // y[lo:hi) visible to the whole CTA
+}
+
+// Partial A[lo:hi, :]^T u[lo:hi) over this CTA's rows for ALL n columns -> pbuf[bid * n + j].
+// Threads own column chunks (coalesced 128-bit loads), loop over the CTA's rows.
+template <typename T>
+__device__ __forceinline__ void grid_matvec_t_partial(const T* __restrict__ A, int n, int lo, int hi,
+                                                      const T* __restrict__ u, T* __restrict__ pout) {
+  constexpr int V = 16 / sizeof(T);
+  using VT = typename V16K<T>::type;
+  const bool vec = (n % V == 0) && ((reinterpret_cast<uintptr_t>(A) & 15) == 0) &&
+                   ((reinterpret_cast<uintptr_t>(pout) & 15) == 0);
+  if (vec) {
+    const int nv = n / V;
+    for (int c = threadIdx.x; c < nv; c += blockDim.x) {
+      T acc[V];
+#pragma unroll
+      for (int e = 0; e < V; ++e) acc[e] = T(0);
+      int i = lo;
+      for (; i + 3 < hi; i += 4) {
+        VT a[4];
+#pragma unroll
+        for (int r = 0; r < 4; ++r) a[r] = ldg_stream(reinterpret_cast<const VT*>(A + (size_t)(i + r) * n) + c);
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+          const T ui = u[i + r];
+          const T* pa = reinterpret_cast<const T*>(&a[r]);
+#pragma unroll
+          for (int e = 0; e < V; ++e) acc[e] = fma_(pa[e], ui, acc[e]);
+        }
+      }
+      for (; i < hi; ++i) {
+        const VT a = ldg_stream(reinterpret_cast<const VT*>(A + (size_t)i * n) + c);
+        const T ui = u[i];
+        const T* pa = reinterpret_cast<const T*>(&a);
+#pragma unroll
+        for (int e = 0; e < V; ++e) acc[e] = fma_(pa[e], ui, acc[e]);
+      }
+      VT o;
+      T* po = reinterpret_cast<T*>(&o);
+#pragma unroll
+      for (int e = 0; e < V; ++e) po[e] = acc[e];
+      reinterpret_cast<VT*>(pout)[c] = o;
+    }
+  } else {
+    for (int j = threadIdx.x; j < n; j += blockDim.x) {
+      T acc = T(0);
+      for (int i = lo; i < hi; ++i) acc = fma_(A[(size_t)i * n + j], u[i], acc);
+      pout[j] = acc;
+    }
+  }
+}
+
+}  // namespace lxb

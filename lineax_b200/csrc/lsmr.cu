@@ -3,6 +3,7 @@
 // Givens rotations, the h / hbar / x updates, the ||r||, ||A||, cond(A) estimates and the
 // four stopping tests all run on chip.  Scalars are carried redundantly by every thread.
 #include "krylov_cta.cuh"
+#include "krylov_grid_api.cuh"
 
 namespace lxb {
 
@@ -202,14 +203,14 @@ __global__ void __launch_bounds__(kKrylovThreads) lsmr_cta_kernel(KrylovParams<T
 }
 
 template <typename T>
-int lsmr_dispatch(KrylovParams<T> p, cudaStream_t st) {
+int lsmr_dispatch(KrylovParams<T> p, void* ws, size_t ws_bytes, cudaStream_t st) {
   if (p.batch < 0 || p.n < 0 || p.m < 0 || !p.A || !p.b || !p.x || !p.result || !p.num_steps)
     return LXB_E_BADARG;
   if (p.batch == 0) return 0;
   const size_t kMax = 227 * 1024;
   const size_t mpad = ((size_t)p.m + 3) & ~(size_t)3, npad = ((size_t)p.n + 3) & ~(size_t)3;
   const size_t vec_bytes = (2 * mpad + 5 * npad + 96) * sizeof(T);
-  if (vec_bytes > kMax) return LXB_E_UNSUPPORTED;
+  if (use_grid_tier(p.batch, p.m, p.n) || vec_bytes > kMax) return lsmr_grid_launch<T>(p, ws, ws_bytes, st);
   const size_t mat_bytes = (size_t)p.m * p.n * sizeof(T);
   p.a_smem = (vec_bytes + mat_bytes <= kMax) && mat_bytes > 0;
   const size_t smem = vec_bytes + (p.a_smem ? mat_bytes : 0);
@@ -233,19 +234,15 @@ int lsmr_dispatch(KrylovParams<T> p, cudaStream_t st) {
                                 int32_t m, int32_t n, T rtol, T atol, T conlim, int64_t max_steps, \
                                 int32_t flags, void* workspace, size_t workspace_bytes,            \
                                 lxb_stream_t stream) {                                             \
-    (void)workspace;                                                                               \
-    (void)workspace_bytes;                                                                         \
     lxb::KrylovParams<T> p{};                                                                      \
     p.A = A; p.sA = stride_A; p.b = b; p.sb = stride_b; p.x = x; p.result = result;                \
     p.num_steps = num_steps; p.stats = stats; p.batch = batch; p.m = m; p.n = n; p.rtol = rtol;    \
     p.atol = atol; p.conlim = conlim; p.max_steps = max_steps; p.flags = flags;                    \
-    return lxb::lsmr_dispatch<T>(p, (cudaStream_t)stream);                                         \
+    return lxb::lsmr_dispatch<T>(p, workspace, workspace_bytes, (cudaStream_t)stream);                                         \
   }                                                                                                \
   extern "C" size_t lxb_lsmr_workspace_##sfx(int64_t batch, int32_t m, int32_t n) {                \
-    (void)batch;                                                                                   \
-    (void)m;                                                                                       \
-    (void)n;                                                                                       \
-    return 0;                                                                                      \
+    const size_t vb = (2 * (((size_t)m + 3) & ~(size_t)3) + 5 * (((size_t)n + 3) & ~(size_t)3) + 96) * sizeof(T); \
+    return (lxb::use_grid_tier(batch, m, n) || vb > 227 * 1024) ? lxb::lsmr_grid_ws_bytes<T>(m, n) : 0; \
   }
 LXB_DEF_LSMR(f32, float)
 LXB_DEF_LSMR(f64, double)
