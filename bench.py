@@ -27,7 +27,10 @@ import numpy as np  # noqa: E402
 WORKLOADS = {
     "lu32": dict(batch=65536, n=32, desc="vmapped lx.LU on 65536 independent 32x32 fp32 systems"),
     "cg256": dict(batch=4096, n=256, desc="vmapped lx.CG on 4096 independent 256x256 SPD fp32 systems, rtol=atol=1e-6"),
+    "gmres32k": dict(batch=1, n=32768, desc="lx.GMRES restart=20 on a 32768x32768 nonsymmetric fp32 dense system, rtol=atol=1e-6"),
+    "lsmr262k": dict(batch=1, n=4096, m=262144, desc="lx.LSMR least squares on a 262144x4096 tall fp32 matrix, rtol=atol=1e-6"),
 }
+LARGE = ("gmres32k", "lsmr262k")
 
 
 def measured_peaks():
@@ -149,6 +152,105 @@ def run_reference(args):
     print(json.dumps(line))
 
 
+def run_large(args, w, rank, local_rank, world):
+    """Single large systems (BASELINE configs[3], configs[4]); with N > 1 every rank solves its own
+    replica (row-sharded NCCL variant not built yet)."""
+    import torch
+    import torch.distributed as dist
+
+    from lineax_b200 import _native as nat
+    from lineax_b200 import _ops
+
+    n = w["n"]
+    m = w.get("m", n)
+    g = torch.Generator(device="cuda").manual_seed(rank)
+    if args.workload == "gmres32k":
+        # reference's easy generator (benchmarks/solver_speeds.py:146-152): N(0,1)/n + 2I
+        A = torch.randn(n, n, generator=g, device="cuda", dtype=torch.float32) / n
+        A.diagonal().add_(2.0)
+        xt = torch.randn(n, generator=g, device="cuda", dtype=torch.float32)
+        b = _ops.matvec(A, xt, False)
+        solve = lambda: _ops.gmres(A, b, None, None, 1e-6, 1e-6, 10 * n, 20, 20, 0)
+        n_mv = lambda k: 1 + 21 * (k - 1)
+        kernel_name = "gmres_grid_kernel<float>"
+    else:
+        A = torch.randn(m, n, generator=g, device="cuda", dtype=torch.float32) / (m ** 0.5)
+        xt = torch.randn(n, generator=g, device="cuda", dtype=torch.float32)
+        b = _ops.matvec(A, xt, False) + 0.1 * torch.randn(m, generator=g, device="cuda", dtype=torch.float32)
+        solve = lambda: _ops.lsmr(A, b, None, 1e-6, 1e-6, 1e8, 10 * n, 0)
+        n_mv = lambda k: 2 + 2 * k
+        kernel_name = "lsmr_grid_kernel<float>"
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        out = solve()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    l0 = nat.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        out = solve()
+    e1.record()
+    barrier()
+    launches = nat.launch_count() - l0
+    clocks = sampler.stop() if rank == 0 else None
+    ms = e0.elapsed_time(e1)
+    t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    k = int(out[2].item())
+    res = int(out[1].item())
+    xerr = float((out[0] - xt).abs().max() / xt.abs().max())
+    alg_bytes = n_mv(k) * m * n * 4
+    peak, peak_src = measured_peaks()
+    achieved = alg_bytes / (ms / args.steps * 1e-3) / 1e9
+    # e2e: host matrix -> device -> solve -> host solution, every step
+    a_pin = A.cpu().pin_memory()
+    b_pin = b.cpu().pin_memory()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    e2e_steps = 2
+    for _ in range(e2e_steps):
+        Ad, bd = a_pin.cuda(non_blocking=True), b_pin.cuda(non_blocking=True)
+        if args.workload == "gmres32k":
+            xo = _ops.gmres(Ad, bd, None, None, 1e-6, 1e-6, 10 * n, 20, 20, 0)[0].cpu()
+        else:
+            xo = _ops.lsmr(Ad, bd, None, 1e-6, 1e-6, 1e8, 10 * n, 0)[0].cpu()
+    dt = time.perf_counter() - t0
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    line = {
+        "metric": f"solves/sec ({w['desc']})", "value": world * args.steps / (ms * 1e-3), "unit": "solves/s",
+        "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": args.workload, "rows": m, "cols": n, "num_steps": k, "result": res,
+                   "rel_err_vs_xtrue": xerr, "parallelism": f"replica x{world}",
+                   "l2": "the 4.3 GB operator is far larger than the 126 MB L2"},
+        "clocks": clocks,
+        "e2e": {"value": world * e2e_steps / dt, "unit": "solves/s", "h2d_bytes_per_step": int(A.numel() * 4 + b.numel() * 4),
+                "d2h_bytes_per_step": int(n * 4), "steps": e2e_steps, "api": "lineax_b200._ops (host pinned -> device -> host)"},
+        "gpu_launches": int(launches),
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                     "traffic": None, "kernel": kernel_name, "peak_source": peak_src,
+                     "algorithmic_bytes_per_launch": alg_bytes, "avg_launch_ms": ms / args.steps},
+        "cpu_baseline": None,
+    }
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -176,6 +278,8 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     w = WORKLOADS[args.workload]
+    if args.workload in LARGE:
+        return run_large(args, w, rank, local_rank, world)
     batch, n = w["batch"], w["n"]
     a_h, b_h = make_inputs(args.workload, rank)  # each rank: its own batch (weak scaling)
     A = torch.as_tensor(a_h).cuda()

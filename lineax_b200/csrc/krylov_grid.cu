@@ -473,6 +473,123 @@ __device__ __forceinline__ void grid_reduce_cols(const GridTeam<T>& team, const 
   }
 }
 
+// Single pass over this CTA's rows of A that produces BOTH Golub-Kahan products:
+//   u'_i   = s1 * (A_i . vin) + s2 * uold_i            (written to unew, rows rlo..rhi)
+//   pout_j = sum_i A_ij u'_i                            (this CTA's partial of A^T u')
+// so A is read from HBM exactly once per LSMR iteration (the reference reads it twice,
+// lsmr.py:214-237; normalising by beta = ||u'|| commutes with the second product).
+// Thread t owns the 16-byte column chunks t, t+256, ... (CH of them) in registers for 4 rows.
+// Returns this CTA's sum of u'_i^2 (identical in every thread).
+template <typename T, int CH>
+__device__ __forceinline__ T lsmr_fused_pass(const T* __restrict__ A, int n, int rlo, int rhi,
+                                             const T* __restrict__ vin, const T* __restrict__ uold,
+                                             T* __restrict__ unew, T s1, T s2, T* __restrict__ pout,
+                                             T* red) {
+  constexpr int V = 16 / sizeof(T);
+  constexpr int R = 4;
+  using VT = typename V16K<T>::type;
+  const int tid = threadIdx.x, nt = blockDim.x;
+  const int nv = n / V;
+  VT v[CH];
+  T acc[CH][V];
+#pragma unroll
+  for (int k = 0; k < CH; ++k) {
+    const int c = tid + k * nt;
+    if (c < nv) {
+      v[k] = reinterpret_cast<const VT*>(vin)[c];
+    } else {
+      T* pz = reinterpret_cast<T*>(&v[k]);
+#pragma unroll
+      for (int e = 0; e < V; ++e) pz[e] = T(0);
+    }
+#pragma unroll
+    for (int e = 0; e < V; ++e) acc[k][e] = T(0);
+  }
+  T ssq = T(0);
+  for (int i0 = rlo; i0 < rhi; i0 += R) {
+    VT a[R][CH];
+    T part[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      const int i = i0 + r < rhi ? i0 + r : rhi - 1;
+      const VT* row = reinterpret_cast<const VT*>(A + (size_t)i * n);
+#pragma unroll
+      for (int k = 0; k < CH; ++k) {
+        const int c = tid + k * nt;
+        if (c < nv) a[r][k] = ldg_stream(row + c);
+        else a[r][k] = v[k];  // v[k] is zero there: contributes nothing
+      }
+    }
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      T d = T(0);
+#pragma unroll
+      for (int k = 0; k < CH; ++k) {
+        const T* pa = reinterpret_cast<const T*>(&a[r][k]);
+        const T* pv = reinterpret_cast<const T*>(&v[k]);
+#pragma unroll
+        for (int e = 0; e < V; ++e) d = fma_(pa[e], pv[e], d);
+      }
+      part[r] = d;
+    }
+    block_sum<T, R>(part, red);
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      const bool valid = i0 + r < rhi;
+      T un = T(0);
+      if (valid) {
+        un = s1 * part[r] + s2 * uold[i0 + r];
+        if (tid == 0) unew[i0 + r] = un;
+        ssq = fma_(un, un, ssq);
+      }
+#pragma unroll
+      for (int k = 0; k < CH; ++k) {
+        const T* pa = reinterpret_cast<const T*>(&a[r][k]);
+#pragma unroll
+        for (int e = 0; e < V; ++e) acc[k][e] = fma_(pa[e], un, acc[k][e]);
+      }
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < CH; ++k) {
+    const int c = tid + k * nt;
+    if (c < nv) {
+      VT o;
+      T* po = reinterpret_cast<T*>(&o);
+#pragma unroll
+      for (int e = 0; e < V; ++e) po[e] = acc[k][e];
+      reinterpret_cast<VT*>(pout)[c] = o;
+    }
+  }
+  return ssq;
+}
+
+template <typename T>
+__device__ __forceinline__ T lsmr_fused_dispatch(int ch, const T* A, int n, int rlo, int rhi,
+                                                 const T* vin, const T* uold, T* unew, T s1, T s2,
+                                                 T* pout, T* red) {
+  switch (ch) {
+    case 1: return lsmr_fused_pass<T, 1>(A, n, rlo, rhi, vin, uold, unew, s1, s2, pout, red);
+    case 2: return lsmr_fused_pass<T, 2>(A, n, rlo, rhi, vin, uold, unew, s1, s2, pout, red);
+    case 3: return lsmr_fused_pass<T, 3>(A, n, rlo, rhi, vin, uold, unew, s1, s2, pout, red);
+    default: return lsmr_fused_pass<T, 4>(A, n, rlo, rhi, vin, uold, unew, s1, s2, pout, red);
+  }
+}
+
+// out[clo:chi) = (sum over CTAs of partials) * inv + out * scale_old   (v update after the fused pass)
+template <typename T>
+__device__ __forceinline__ void grid_reduce_cols_scaled(const GridTeam<T>& team, const T* pbuf, int n,
+                                                        int clo, int chi, T* out, T inv_div,
+                                                        T scale_old) {
+  const int lane = team.tid & 31, warp = team.tid >> 5, nw = team.nt >> 5;
+  for (int j = clo + warp; j < chi; j += nw) {
+    T acc = T(0);
+    for (int b = lane; b < team.nb; b += 32) acc += __ldcg(pbuf + (size_t)b * n + j);
+    acc = warp_sum(acc);
+    if (lane == 0) out[j] = out[j] * scale_old + acc / inv_div;
+  }
+}
+
 template <typename T>
 __global__ void __launch_bounds__(kGridThreads) lsmr_grid_kernel(KrylovParams<T> p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -493,10 +610,15 @@ __global__ void __launch_bounds__(kGridThreads) lsmr_grid_kernel(KrylovParams<T>
   team.slice(n, clo, chi);
   const int tid = team.tid, nt = team.nt;
   const bool has_scale = !(p.rtol == T(0) && p.atol == T(0));
+  constexpr int V = 16 / sizeof(T);
+  const int ch = (n / V + nt - 1) / nt;  // 16-byte column chunks per thread
 
   for (int64_t sys = 0; sys < p.batch; ++sys) {
     const T* A = p.A + sys * p.sA;
     const T* b = p.b + sys * p.sb;
+    // one-read-of-A path: rows must fit the per-thread register tile and be 16-byte aligned
+    const bool fused = (n % V == 0) && ch >= 1 && ch <= 4 &&
+                       ((reinterpret_cast<uintptr_t>(A) & 15) == 0) && !(p.flags & (1 << 30));
     for (int i = clo + tid; i < chi; i += nt) {
       wx[i] = (p.flags & LXB_HAS_Y0) ? p.x[sys * n + i] : T(0);
       whb[i] = T(0);
@@ -505,19 +627,35 @@ __global__ void __launch_bounds__(kGridThreads) lsmr_grid_kernel(KrylovParams<T>
     for (int i = rlo + tid; i < rhi; i += nt) wu[i] = b[i];
     __syncthreads();
     const T normb = grid_norm2<T>(team, wu, rlo, rhi, m);  // barrier: x visible
-    grid_matvec<T>(A, n, rlo, rhi, wx, wt, T(1));
-    for (int i = rlo + tid; i < rhi; i += nt) wu[i] = wu[i] - wt[i];
-    __syncthreads();
-    T beta = grid_norm2<T>(team, wu, rlo, rhi, m);
-    T alpha = T(0);
-    if (beta != T(0)) {
-      for (int i = rlo + tid; i < rhi; i += nt) wu[i] = wu[i] / beta;
+    T beta, alpha = T(0);
+    if (fused) {
+      // u' = b - A x0 and A^T u' from one read of A
+      T sq[1];
+      sq[0] = lsmr_fused_dispatch<T>(ch, A, n, rlo, rhi, wx, wu, wu, T(-1), T(1),
+                                     pbuf + (size_t)team.bid * npad, red);
+      if (tid != 0) sq[0] = T(0);
+      team.template reduce<1, 0>(sq, nullptr);  // barrier: partials visible
+      beta = m == 1 ? abs_(wu[0]) : sqrt_(sq[0]);
+      if (beta != T(0)) {
+        for (int i = rlo + tid; i < rhi; i += nt) wu[i] = wu[i] / beta;
+        grid_reduce_cols_scaled<T>(team, pbuf, (int)npad, clo, chi, wv, beta, T(0));
+        __syncthreads();
+        alpha = grid_norm2<T>(team, wv, clo, chi, n);
+      }
+    } else {
+      grid_matvec<T>(A, n, rlo, rhi, wx, wt, T(1));
+      for (int i = rlo + tid; i < rhi; i += nt) wu[i] = wu[i] - wt[i];
       __syncthreads();
-      grid_matvec_t_partial<T>(A, n, rlo, rhi, wu, pbuf + (size_t)team.bid * npad);
-      team.sync();
-      grid_reduce_cols<T>(team, pbuf, (int)npad, clo, chi, wv, T(0));
-      __syncthreads();
-      alpha = grid_norm2<T>(team, wv, clo, chi, n);
+      beta = grid_norm2<T>(team, wu, rlo, rhi, m);
+      if (beta != T(0)) {
+        for (int i = rlo + tid; i < rhi; i += nt) wu[i] = wu[i] / beta;
+        __syncthreads();
+        grid_matvec_t_partial<T>(A, n, rlo, rhi, wu, pbuf + (size_t)team.bid * npad);
+        team.sync();
+        grid_reduce_cols<T>(team, pbuf, (int)npad, clo, chi, wv, T(0));
+        __syncthreads();
+        alpha = grid_norm2<T>(team, wv, clo, chi, n);
+      }
     }
     {
       const T den = alpha == T(0) ? T(1) : alpha;
@@ -540,20 +678,37 @@ __global__ void __launch_bounds__(kGridThreads) lsmr_grid_kernel(KrylovParams<T>
     while (istop == 0) {
       itn += 1;
       team.sync();  // v complete
-      grid_matvec<T>(A, n, rlo, rhi, wv, wt, T(1));
-      for (int i = rlo + tid; i < rhi; i += nt) wu[i] = wu[i] * -alpha + wt[i];
-      __syncthreads();
-      beta = grid_norm2<T>(team, wu, rlo, rhi, m);
-      if (beta != T(0)) {
-        for (int i = rlo + tid; i < rhi; i += nt) wu[i] = wu[i] / beta;
+      if (fused) {
+        T sq[1];
+        sq[0] = lsmr_fused_dispatch<T>(ch, A, n, rlo, rhi, wv, wu, wu, T(1), -alpha,
+                                       pbuf + (size_t)team.bid * npad, red);
+        if (tid != 0) sq[0] = T(0);
+        team.template reduce<1, 0>(sq, nullptr);
+        beta = m == 1 ? abs_(wu[0]) : sqrt_(sq[0]);
+        if (beta != T(0)) {
+          for (int i = rlo + tid; i < rhi; i += nt) wu[i] = wu[i] / beta;
+          grid_reduce_cols_scaled<T>(team, pbuf, (int)npad, clo, chi, wv, beta, -beta);
+          __syncthreads();
+          alpha = grid_norm2<T>(team, wv, clo, chi, n);
+          const T den = alpha == T(0) ? T(1) : alpha;
+          for (int i = clo + tid; i < chi; i += nt) wv[i] = wv[i] / den;
+        }
+      } else {
+        grid_matvec<T>(A, n, rlo, rhi, wv, wt, T(1));
+        for (int i = rlo + tid; i < rhi; i += nt) wu[i] = wu[i] * -alpha + wt[i];
         __syncthreads();
-        grid_matvec_t_partial<T>(A, n, rlo, rhi, wu, pbuf + (size_t)team.bid * npad);
-        team.sync();
-        grid_reduce_cols<T>(team, pbuf, (int)npad, clo, chi, wv, -beta);
-        __syncthreads();
-        alpha = grid_norm2<T>(team, wv, clo, chi, n);
-        const T den = alpha == T(0) ? T(1) : alpha;
-        for (int i = clo + tid; i < chi; i += nt) wv[i] = wv[i] / den;
+        beta = grid_norm2<T>(team, wu, rlo, rhi, m);
+        if (beta != T(0)) {
+          for (int i = rlo + tid; i < rhi; i += nt) wu[i] = wu[i] / beta;
+          __syncthreads();
+          grid_matvec_t_partial<T>(A, n, rlo, rhi, wu, pbuf + (size_t)team.bid * npad);
+          team.sync();
+          grid_reduce_cols<T>(team, pbuf, (int)npad, clo, chi, wv, -beta);
+          __syncthreads();
+          alpha = grid_norm2<T>(team, wv, clo, chi, n);
+          const T den = alpha == T(0) ? T(1) : alpha;
+          for (int i = clo + tid; i < chi; i += nt) wv[i] = wv[i] / den;
+        }
       }
       T chat, shat, alphahat;
       givens_g<T>(alphabar, T(0), chat, shat, alphahat);
