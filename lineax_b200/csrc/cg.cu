@@ -3,6 +3,9 @@
 // stabilise_every true-residual recompute all run inside the kernel, each system exits
 // as soon as its own test passes (observably equal to JAX's masked lock-step loop,
 // SURVEY.md App. B-3).
+#include <type_traits>
+
+#include "cg_resident.cuh"
 #include "krylov_cta.cuh"
 #include "krylov_grid_api.cuh"
 
@@ -116,6 +119,10 @@ int cg_dispatch(KrylovParams<T> p, void* ws, size_t ws_bytes, cudaStream_t st) {
   const size_t npad = ((size_t)p.n + 3) & ~(size_t)3;
   const size_t vec_bytes = (6 * npad + 96) * sizeof(T);
   if (use_grid_tier(p.batch, p.n, p.n) || vec_bytes > kMaxSmemK) return cg_grid_launch<T>(p, ws, ws_bytes, st);
+  if constexpr (std::is_same<T, float>::value) {
+    // 256x256 fp32: operator resident in registers + shared memory for the whole solve
+    if (cg_resident_applicable(p) && !getenv("LXB_NO_RESIDENT")) return cg_resident_launch(p, st);
+  }
   const size_t mat_bytes = (size_t)p.n * p.n * sizeof(T);
   p.a_smem = (vec_bytes + mat_bytes <= kMaxSmemK) && p.n > 0;
   const size_t smem = vec_bytes + (p.a_smem ? mat_bytes : 0);
