@@ -208,6 +208,29 @@ LXB_DECL_KRYLOV(f64, double)
 LXB_DECL_VEC(f32, float)
 LXB_DECL_VEC(f64, double)
 
+/* ------------------------------------------------ multi-GPU, row-sharded --
+ * Restarted GMRES on ONE large system partitioned by rows over the GPUs of an NVLink box
+ * (one process per GPU).  Rank r owns rows [row_offset, row_offset + n_local) of A
+ * (A_local[n_local, n] row-major) and the same slice of b / x.  The per-step all-gather of the
+ * Krylov vector and all-reduce of the Gram-Schmidt scalars are fused into the persistent kernel
+ * over peer memory: peer_buffers is a DEVICE array of `world` pointers to every rank's symmetric
+ * buffer (lxb_gmres_rowsharded_symm_bytes_* bytes each, zero-initialised once, e.g. from
+ * torch.distributed._symmetric_memory).  All ranks must call with identical scalar arguments;
+ * result / num_steps (1 element) are identical on every rank.
+ */
+#define LXB_DECL_GMRES_DIST(sfx, T)                                                                 \
+  int lxb_gmres_rowsharded_##sfx(const T* A_local, const T* b_local, T* x_local, int32_t* result,  \
+                                 int32_t* num_steps, int32_t n, int32_t n_local,                   \
+                                 int32_t row_offset, T rtol, T atol, int32_t max_steps,            \
+                                 int32_t restart, int32_t stagnation_iters, int32_t flags,         \
+                                 void* workspace, size_t workspace_bytes,                          \
+                                 void* const* peer_buffers, int32_t world, int32_t rank,           \
+                                 lxb_stream_t stream);                                             \
+  size_t lxb_gmres_rowsharded_workspace_##sfx(int32_t n_local, int32_t restart);                   \
+  size_t lxb_gmres_rowsharded_symm_bytes_##sfx(int32_t n);
+LXB_DECL_GMRES_DIST(f32, float)
+LXB_DECL_GMRES_DIST(f64, double)
+
 /* ------------------------------------------------------ post-processing --
  * lineax/_solve.py:104-123, per system:
  *   successful & any(!isfinite(x)) -> singular;  singular & any(!isfinite(b)) -> nonfinite_input.

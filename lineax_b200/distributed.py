@@ -1,0 +1,70 @@
+"""Row-sharded solves of ONE large system across the GPUs of an NVLink box.
+
+One process per GPU (`torch.distributed`, NCCL for the rendezvous only).  The data-path exchanges
+(all-gather of the Krylov vector, all-reduce of the Gram-Schmidt scalars) are NOT NCCL calls: they
+are fused into the persistent solver kernel over peer memory obtained from
+`torch.distributed._symmetric_memory` (csrc/gmres_dist.cu).
+"""
+from __future__ import annotations
+
+import torch
+import torch.distributed as dist
+
+from . import _native as nat
+from ._shard import shard_bounds
+
+
+class RowShardedGMRES:
+    """Restarted GMRES (lineax/_solver/gmres.py semantics) on a row-partitioned dense operator.
+
+    Every rank constructs it with the same arguments and then calls `solve(A_local, b_local)` with
+    its contiguous block of rows (`row_range(rank)`); returns `(x_local, result, num_steps)`.
+    """
+
+    def __init__(self, n: int, rtol: float, atol: float, *, restart: int = 20, stagnation_iters: int = 20,
+                 max_steps=None, dtype=torch.float32, group=None):
+        import torch.distributed._symmetric_memory as symm
+
+        self.n, self.rtol, self.atol = int(n), float(rtol), float(atol)
+        self.restart, self.stagnation_iters, self.max_steps = int(restart), int(stagnation_iters), max_steps
+        self.dtype, self.group = dtype, group if group is not None else dist.group.WORLD
+        self.world, self.rank = dist.get_world_size(self.group), dist.get_rank(self.group)
+        self.bounds = shard_bounds(self.n, self.world)
+        self.sfx = nat.suffix(dtype)
+        self.device = torch.device("cuda", torch.cuda.current_device())
+        nbytes = nat.fn(f"lxb_gmres_rowsharded_symm_bytes_{self.sfx}")(self.n)
+        self.symm_buf = symm.empty(nbytes, dtype=torch.uint8, device=self.device)
+        self.symm_buf.zero_()
+        self.handle = symm.rendezvous(self.symm_buf, self.group)
+        self.peers_dev = int(self.handle.buffer_ptrs_dev)
+        torch.cuda.synchronize()
+        dist.barrier(self.group)  # every rank's flags are zero before the first kernel starts
+
+    def row_range(self, rank=None):
+        r = self.rank if rank is None else rank
+        return self.bounds[r], self.bounds[r + 1]
+
+    def solve(self, a_local: torch.Tensor, b_local: torch.Tensor, y0_local: torch.Tensor | None = None):
+        lo, hi = self.row_range()
+        nl = hi - lo
+        if tuple(a_local.shape) != (nl, self.n) or tuple(b_local.shape) != (nl,):
+            raise ValueError(f"rank {self.rank}: expected A_local {(nl, self.n)} and b_local {(nl,)}")
+        a_local = a_local.to(self.dtype).contiguous()
+        b_local = b_local.to(self.dtype).contiguous()
+        flags = 0 if self.max_steps is None else nat.MAXSTEPS_GIVEN
+        ms = 10 * self.n if self.max_steps is None else int(self.max_steps)
+        restart = min(self.restart, self.n)
+        if y0_local is not None:
+            x = y0_local.to(self.dtype).contiguous().clone()
+            flags |= nat.HAS_Y0
+        else:
+            x = torch.empty(nl, dtype=self.dtype, device=self.device)
+        result = torch.empty(1, dtype=torch.int32, device=self.device)
+        steps = torch.empty(1, dtype=torch.int32, device=self.device)
+        ws_bytes = nat.fn(f"lxb_gmres_rowsharded_workspace_{self.sfx}")(nl, restart)
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=self.device)
+        nat.call(f"lxb_gmres_rowsharded_{self.sfx}", a_local.data_ptr(), b_local.data_ptr(), x.data_ptr(),
+                 result.data_ptr(), steps.data_ptr(), self.n, nl, lo, self.rtol, self.atol, ms, restart,
+                 self.stagnation_iters, flags, ws.data_ptr(), ws_bytes, self.peers_dev, self.world, self.rank,
+                 torch.cuda.current_stream().cuda_stream)
+        return x, result[0], steps[0]
