@@ -153,8 +153,9 @@ def run_reference(args):
 
 
 def run_large(args, w, rank, local_rank, world):
-    """Single large systems (BASELINE configs[3], configs[4]); with N > 1 every rank solves its own
-    replica (row-sharded NCCL variant not built yet)."""
+    """Single large systems (BASELINE configs[3], configs[4]).  gmres32k with N > 1: ONE system
+    row-sharded over the ranks (strong scaling, exchanges fused into the kernel over NVLink);
+    lsmr262k with N > 1: every rank solves its own replica."""
     import torch
     import torch.distributed as dist
 
@@ -164,7 +165,12 @@ def run_large(args, w, rank, local_rank, world):
     n = w["n"]
     m = w.get("m", n)
     g = torch.Generator(device="cuda").manual_seed(rank)
-    sharded = args.workload == "gmres32k" and world > 1
+    force = os.environ.get("LXB_FORCE_SHARDED") == "1"  # experiment: dist kernel on a 1-rank group
+    sharded = args.workload == "gmres32k" and (world > 1 or force)
+    if force and world == 1 and not dist.is_initialized():
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ.setdefault("MASTER_PORT", "29577")
+        dist.init_process_group("nccl", rank=0, world_size=1, device_id=torch.device("cuda", local_rank))
     if sharded:
         # ONE system row-partitioned over the ranks (strong scaling); exchanges fused in the kernel
         from lineax_b200.distributed import RowShardedGMRES
@@ -186,6 +192,14 @@ def run_large(args, w, rank, local_rank, world):
         n_mv = lambda k: 1 + 21 * (k - 1)
         kernel_name = "gmres_dist_kernel<float>"
     elif args.workload == "gmres32k":
+        # reference's easy generator (benchmarks/solver_speeds.py:146-152): N(0,1)/n + 2I
+        A = torch.randn(n, n, generator=g, device="cuda", dtype=torch.float32) / n
+        A.diagonal().add_(2.0)
+        xt = torch.randn(n, generator=g, device="cuda", dtype=torch.float32)
+        b = _ops.matvec(A, xt, False)
+        solve = lambda: _ops.gmres(A, b, None, None, 1e-6, 1e-6, 10 * n, 20, 20, 0)
+        n_mv = lambda k: 1 + 21 * (k - 1)
+        kernel_name = "gmres_grid_kernel<float>"
     else:
         A = torch.randn(m, n, generator=g, device="cuda", dtype=torch.float32) / (m ** 0.5)
         xt = torch.randn(n, generator=g, device="cuda", dtype=torch.float32)

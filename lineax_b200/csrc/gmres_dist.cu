@@ -16,6 +16,7 @@
 namespace lxb {
 
 constexpr int kMaxPeers = 16;
+constexpr int kDistThreads = 512;  // 16 warps per CTA: one CTA per SM when x is staged in shared memory
 constexpr size_t kSymmFlagBytes = 4096;  // [0]: persistent epoch, [64 + 16*r]: arrival slot of rank r
 
 __host__ __device__ inline size_t symm_part_off() { return kSymmFlagBytes; }
@@ -40,26 +41,68 @@ struct DistTeam {
     epoch = *reinterpret_cast<volatile unsigned long long*>(mine);
   }
 
-  // Cross-GPU barrier. All remote stores issued by any thread of this GPU before the call are
-  // visible to every peer after it (threads fence at system scope before the grid barrier).
-  __device__ void xsync() {
-    __threadfence_system();
+  // ONE fused round = grid-wide + cross-GPU all-reduce of KS sums and KM abs-maxima AND a
+  // cross-GPU barrier for every remote store issued before it (vector pushes):
+  //   per-CTA partials -> local buffer -> grid barrier -> CTA 0 folds them and pushes this GPU's
+  //   totals into a slot of every peer -> epoch flags (release.sys) -> every CTA polls its own
+  //   GPU's flags (acquire.sys) -> every CTA folds the P slots in rank order.
+  // `sums` / `maxes` live in shared memory and hold this CTA's block-reduced values on entry,
+  // the global results on exit (identical bits on every CTA of every GPU).
+  __device__ void xround(T* sums, int KS, T* maxes, int KM) {
+    const int K = KS + KM;
+    T* lbuf = g.part + (size_t)g.flip * kGridMaxK * g.nb;
+    g.flip ^= 1;
+    const size_t off = symm_part_off() + (size_t)xflip * kGridMaxK * kMaxPeers * sizeof(T);
+    xflip ^= 1;
+    __syncthreads();
+    for (int k = g.tid; k < K; k += g.nt) lbuf[(size_t)k * g.nb + g.bid] = k < KS ? sums[k] : maxes[k - KS];
+    __threadfence_system();  // also orders this thread's earlier remote pushes
     g.sync();
     epoch += 1;
-    if (g.bid == 0 && g.tid < P) {
-      unsigned long long* slot = reinterpret_cast<unsigned long long*>(peers[g.tid] + 64 + 16 * rank);
-      asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(slot), "l"(epoch) : "memory");
+    if (g.bid == 0) {
+      const int lane = g.tid & 31, warp = g.tid >> 5, nw = g.nt >> 5;
+      for (int k = warp; k < K; k += nw) {
+        T a = T(0);
+        if (k < KS) {
+          for (int i = lane; i < g.nb; i += 32) a += __ldcg(lbuf + (size_t)k * g.nb + i);
+          a = warp_sum(a);
+        } else {
+          for (int i = lane; i < g.nb; i += 32) a = absmax2(a, __ldcg(lbuf + (size_t)k * g.nb + i));
+          a = warp_absmax(a);
+        }
+        if (lane < P) reinterpret_cast<T*>(peers[lane] + off)[(size_t)k * kMaxPeers + rank] = a;
+      }
+      __threadfence_system();
+      __syncthreads();
+      if (g.tid < P) {
+        unsigned long long* slot = reinterpret_cast<unsigned long long*>(peers[g.tid] + 64 + 16 * rank);
+        asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(slot), "l"(epoch) : "memory");
+      }
+    }
+    if (g.tid < P) {
       const unsigned long long* my = reinterpret_cast<const unsigned long long*>(mine + 64 + 16 * g.tid);
       unsigned long long seen;
       do {
         asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(seen) : "l"(my) : "memory");
       } while (seen < epoch);
     }
-    g.sync();
+    __syncthreads();
+    const T* in = reinterpret_cast<const T*>(mine + off);
+    for (int k = g.tid; k < K; k += g.nt) {
+      T a = T(0);
+      if (k < KS) {
+        for (int q = 0; q < P; ++q) a += __ldcg(in + (size_t)k * kMaxPeers + q);
+        sums[k] = a;
+      } else {
+        for (int q = 0; q < P; ++q) a = absmax2(a, __ldcg(in + (size_t)k * kMaxPeers + q));
+        maxes[k - KS] = a;
+      }
+    }
+    __syncthreads();
   }
 
   // push my slice [lo, hi) (local indices) of a vector into every GPU's exchange buffer at the
-  // global position; followed by xsync() the full vector is readable locally at xchg().
+  // global position; readable locally at xchg() after the next xround().
   __device__ T* xchg() const { return reinterpret_cast<T*>(mine + symm_xchg_off<T>()); }
   __device__ void push(const T* local, int lo, int hi, int row_offset) {
     for (int q = 0; q < P; ++q) {
@@ -67,41 +110,9 @@ struct DistTeam {
       for (int i = lo + g.tid; i < hi; i += g.nt) dst[i] = local[i];
     }
   }
-
-  // global all-reduce of K sums held in shared memory `vals` (already summed over this GPU)
-  __device__ void xreduce_sum(T* vals, int K) {
-    T* slotbase = nullptr;
-    const size_t off = symm_part_off() + (size_t)xflip * kGridMaxK * kMaxPeers * sizeof(T);
-    xflip ^= 1;
-    if (g.bid == 0) {
-      for (int idx = g.tid; idx < K * P; idx += g.nt) {
-        const int q = idx / K, k = idx % K;
-        slotbase = reinterpret_cast<T*>(peers[q] + off);
-        slotbase[(size_t)k * kMaxPeers + rank] = vals[k];
-      }
-    }
-    xsync();
-    const T* in = reinterpret_cast<const T*>(mine + off);
-    __syncthreads();
-    for (int k = g.tid; k < K; k += g.nt) {
-      T s = T(0);
-      for (int q = 0; q < P; ++q) s += __ldcg(in + (size_t)k * kMaxPeers + q);
-      vals[k] = s;
-    }
-    __syncthreads();
-  }
-  __device__ T xreduce_max1(T v) {  // NaN-propagating abs-max of one value per GPU
-    const size_t off = symm_part_off() + (size_t)xflip * kGridMaxK * kMaxPeers * sizeof(T);
-    xflip ^= 1;
-    if (g.bid == 0 && g.tid < P) reinterpret_cast<T*>(peers[g.tid] + off)[rank] = v;
-    xsync();
-    const T* in = reinterpret_cast<const T*>(mine + off);
-    T m = T(0);
-    for (int q = 0; q < P; ++q) m = absmax2(m, __ldcg(in + q));
-    return m;
-  }
-  __device__ void finish() {
-    xsync();  // nobody leaves (and starts overwriting exchange slots) while a peer still reads
+  __device__ void finish(T* scratch) {
+    xround(scratch, 0, scratch, 0);  // nobody leaves (and reuses exchange slots) while a peer still reads
+    g.sync();
     if (g.bid == 0 && g.tid == 0) *reinterpret_cast<volatile unsigned long long*>(mine) = epoch;
   }
 };
@@ -110,15 +121,8 @@ template <typename T>
 struct DistParams {
   KrylovParams<T> k;
   unsigned char* const* peers;
-  int world, rank, n_global, row_offset;
+  int world, rank, n_global, row_offset, stage_x;
 };
-
-// local + global dot over the distributed vector slices
-template <typename T>
-__device__ __forceinline__ void dist_sums(DistTeam<T>& t, T* vals_smem, int K) {
-  t.g.reduce_dyn(vals_smem, K);  // over this GPU's CTAs
-  t.xreduce_sum(vals_smem, K);   // over GPUs
-}
 
 template <typename T>
 __device__ void cta_hessenberg_lstsq_d(T* Q, T* rhs, T* z, int R, T* sc) {
@@ -164,7 +168,7 @@ __device__ void cta_hessenberg_lstsq_d(T* Q, T* rhs, T* z, int R, T* sc) {
 }
 
 template <typename T>
-__global__ void __launch_bounds__(kGridThreads) gmres_dist_kernel(DistParams<T> dp) {
+__global__ void __launch_bounds__(kDistThreads) gmres_dist_kernel(DistParams<T> dp) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const KrylovParams<T>& p = dp.k;
   const int n = dp.n_global, nl = p.n /* local rows */, R = p.restart, off = dp.row_offset;
@@ -175,6 +179,9 @@ __global__ void __launch_bounds__(kGridThreads) gmres_dist_kernel(DistParams<T> 
   T* coeff = rhs + kGridMaxK;
   T* Qm = coeff + (size_t)R * (R + 1);
   T* sc = Qm + (size_t)R * (R + 1);
+  // optional staging area for the assembled matvec input (the symmetric exchange buffer is not
+  // L1-cacheable): present when the launcher found room for n elements
+  T* xs = dp.stage_x ? reinterpret_cast<T*>((reinterpret_cast<uintptr_t>(sc + 8) + 15) & ~(uintptr_t)15) : nullptr;
   const size_t lpad = ((size_t)nl + 3) & ~(size_t)3;
   T* part = p.ws;
   DistTeam<T> team(part, red, dp.peers, dp.world, dp.rank);
@@ -193,33 +200,34 @@ __global__ void __launch_bounds__(kGridThreads) gmres_dist_kernel(DistParams<T> 
   const T* b = p.b;  // [nl]
   T* xfull = team.xchg();
 
-  auto not_converged = [&](bool diff_inf) -> bool {
-    if (!has_scale) {
-      team.xsync();
-      return true;
-    }
-    T v[2] = {T(0), T(0)};
+  // block-level partial of a dot over this CTA's slice -> smem slot
+  auto cta_dot_to = [&](const T* a, const T* c, T* slot) {
+    T v[1] = {T(0)};
+    for (int i = lo + tid; i < hi; i += nt) v[0] = fma_(a[i], c[i], v[0]);
+    block_sum<T, 1>(v, red);
+    if (tid == 0) *slot = v[0];
+  };
+  // residual r = b - A y (y assembled in the exchange buffer) and the three max-norms the loop
+  // needs: mx[0] = max|r| (stagnation), mx[1], mx[2] = the convergence test of gmres.py:130-141
+  T* mx = zv;  // 3 slots of shared scratch (zv is only live inside the least-squares solve)
+  auto residual_and_norms = [&](bool diff_inf) {
+    team.push(wy, lo, hi, off);
+    team.xround(sc, 0, sc, 0);  // y assembled everywhere
+    grid_matvec<T>(A, n, lo, hi, xfull, ww, T(1), xs);
+    T v[3] = {T(0), T(0), T(0)};
     for (int i = lo + tid; i < hi; i += nt) {
+      const T r = b[i] - ww[i];
+      wr[i] = r;
       const T bs = p.atol + p.rtol * abs_(b[i]);
       const T ys = p.atol + p.rtol * abs_(wy[i]);
       const T d = diff_inf ? Num<T>::inf() : wd[i];
-      v[0] = absmax2(v[0], wr[i] / bs);
-      v[1] = absmax2(v[1], d / ys);
+      v[0] = absmax2(v[0], r);
+      v[1] = absmax2(v[1], r / bs);
+      v[2] = absmax2(v[2], d / ys);
     }
-    g.template reduce<0, 2>(nullptr, v);
-    const T m0 = team.xreduce_max1(v[0]);
-    const T m1 = team.xreduce_max1(v[1]);
-    return (m0 > T(1)) || (m1 > T(1));
-  };
-  // global two-norm of a distributed vector (size-1 shortcut on the GLOBAL size)
-  auto norm2 = [&](const T* a) -> T {
-    T s[1] = {T(0)};
-    for (int i = lo + tid; i < hi; i += nt) s[0] = fma_(a[i], a[i], s[0]);
-    g.template reduce<1, 0>(s, nullptr);
-    if (tid == 0) sc[2] = s[0];
-    __syncthreads();
-    team.xreduce_sum(sc + 2, 1);
-    return sqrt_(sc[2]);  // (n == 1: sqrt(x^2) = |x|, the _norm.py:74-80 shortcut)
+    block_absmax<T, 3>(v, red);
+    if (tid == 0) { mx[0] = v[0]; mx[1] = v[1]; mx[2] = v[2]; }
+    team.xround(sc, 0, mx, 3);
   };
 
   for (int i = lo + tid; i < hi; i += nt) {
@@ -227,32 +235,35 @@ __global__ void __launch_bounds__(kGridThreads) gmres_dist_kernel(DistParams<T> 
     wr[i] = T(0);
   }
   __syncthreads();
-  bool breakdown = false, deferred = false, diff_inf = true;
+  bool breakdown = false, deferred = false, diff_inf = true, nc = true;
   T r_min = Num<T>::inf();
   int64_t step = 0;
   int stag = 0;
   while (true) {
-    bool go = !deferred && stag < p.stagnation_iters;
-    const bool nc = not_converged(diff_inf);
-    go = (go && nc && step < p.max_steps) || step == 0;
+    // cond_fun, gmres.py:143-158 (`nc` was evaluated on the current state at the end of the
+    // previous pass; it is irrelevant at step 0)
+    const bool go = (!deferred && stag < p.stagnation_iters && nc && step < p.max_steps) || step == 0;
     if (!go) break;
     bool bd_new = false;
     if (step > 0) {
-      const T beta0 = norm2(wr);
+      // V[0] = r / ||r||: the UNNORMALISED slice goes into the exchange buffer together with the
+      // norm partial (one round); consumers scale the matvec by 1/||r|| instead
+      team.push(wr, lo, hi, off);
+      cta_dot_to(wr, wr, sc + 2);
+      team.xround(sc + 2, 1, sc, 0);
+      const T beta0 = sqrt_(sc[2]);
       const bool init_bd = beta0 < eps;
-      const T safe0 = init_bd ? Num<T>::inf() : beta0;
+      T safe = init_bd ? Num<T>::inf() : beta0;
       for (int i = lo + tid; i < hi; i += nt) {
-        V[i] = wr[i] / safe0;
+        V[i] = wr[i] / safe;
         for (int j = 1; j <= R; ++j) V[(size_t)j * lpad + i] = T(0);
       }
       for (int idx = tid; idx < R * (R + 1); idx += nt)
         coeff[idx] = (idx / (R + 1) == idx % (R + 1)) ? T(1) : T(0);
       __syncthreads();
-      team.push(V, lo, hi, off);
-      team.xsync();  // V[0] assembled in every GPU's exchange buffer
       bd_new = init_bd;
       for (int k = 0; k < R && !bd_new; ++k) {
-        grid_matvec<T>(A, n, lo, hi, xfull, ww, T(1));
+        grid_matvec<T>(A, n, lo, hi, xfull, ww, T(1) / safe, xs);
         {
           const int lane = tid & 31, warp = tid >> 5, nw = nt >> 5;
           for (int j = warp; j <= R + 1; j += nw) {
@@ -263,7 +274,7 @@ __global__ void __launch_bounds__(kGridThreads) gmres_dist_kernel(DistParams<T> 
             if (lane == 0) proj[j] = a;
           }
         }
-        dist_sums<T>(team, proj, R + 2);
+        team.xround(proj, R + 2, sc, 0);
         const T step_norm = sqrt_(proj[R + 1]);
         for (int i = lo + tid; i < hi; i += nt) {
           T acc = T(0);
@@ -271,14 +282,15 @@ __global__ void __launch_bounds__(kGridThreads) gmres_dist_kernel(DistParams<T> 
           ww[i] = ww[i] - acc;
         }
         __syncthreads();
-        const T nrm = norm2(ww);
+        team.push(ww, lo, hi, off);  // next Krylov vector, unnormalised
+        cta_dot_to(ww, ww, sc + 2);
+        team.xround(sc + 2, 1, sc, 0);
+        const T nrm = sqrt_(sc[2]);
         bd_new = nrm < step_norm * eps;
-        const T safe = bd_new ? Num<T>::inf() : nrm;
+        safe = bd_new ? Num<T>::inf() : nrm;
         for (int i = lo + tid; i < hi; i += nt) V[(size_t)(k + 1) * lpad + i] = ww[i] / safe;
         for (int j = tid; j <= R; j += nt) coeff[k * (R + 1) + j] = (j == k + 1) ? nrm : proj[j];
         __syncthreads();
-        team.push(V + (size_t)(k + 1) * lpad, lo, hi, off);
-        team.xsync();
       }
       for (int idx = tid; idx < (R + 1) * R; idx += nt) {
         const int i = idx / R, c = idx % R;
@@ -296,15 +308,10 @@ __global__ void __launch_bounds__(kGridThreads) gmres_dist_kernel(DistParams<T> 
       diff_inf = false;
       __syncthreads();
     }
-    team.push(wy, lo, hi, off);
-    team.xsync();  // y assembled everywhere
-    grid_matvec<T>(A, n, lo, hi, xfull, ww, T(1));
-    for (int i = lo + tid; i < hi; i += nt) wr[i] = b[i] - ww[i];
+    residual_and_norms(diff_inf);
+    const T rn = mx[0];
+    nc = !has_scale || (mx[1] > T(1)) || (mx[2] > T(1));
     __syncthreads();
-    T mx[1] = {T(0)};
-    for (int i = lo + tid; i < hi; i += nt) mx[0] = absmax2(mx[0], wr[i]);
-    g.template reduce<0, 1>(nullptr, mx);
-    const T rn = team.xreduce_max1(mx[0]);
     const bool decreased = (rn - r_min) < T(0);
     stag = decreased ? 0 : stag + 1;
     r_min = (rn < r_min || rn != rn) ? rn : r_min;
@@ -314,14 +321,13 @@ __global__ void __launch_bounds__(kGridThreads) gmres_dist_kernel(DistParams<T> 
   }
   int result = krylov_final_result(step, p.max_steps, p.flags, has_scale);
   if (stag >= p.stagnation_iters) result = LXB_STAGNATION;
-  const bool nc = not_converged(diff_inf);
   if (deferred && nc) result = LXB_BREAKDOWN;
   for (int i = lo + tid; i < hi; i += nt) p.x[i] = wy[i];
   if (g.bid == 0 && tid == 0) {
     p.result[0] = result;
     p.num_steps[0] = (int32_t)step;
   }
-  team.finish();
+  team.finish(sc);
 }
 
 template <typename T>
@@ -347,18 +353,21 @@ int gmres_dist_launch(const T* A_local, const T* b_local, T* x_local, int32_t* r
   dp.k.flags = flags; dp.k.ws = reinterpret_cast<T*>(ws);
   dp.peers = reinterpret_cast<unsigned char* const*>(peers);
   dp.world = world; dp.rank = rank; dp.n_global = n; dp.row_offset = row_offset;
-  const size_t smem = (96 + 4 * kGridMaxK + 2 * (size_t)restart * (restart + 1) + 8) * sizeof(T);
+  size_t smem = (96 + 4 * kGridMaxK + 2 * (size_t)restart * (restart + 1) + 8) * sizeof(T) + 16;
+  const size_t xbytes = pad4(n) * sizeof(T);
+  dp.stage_x = smem + xbytes <= 200 * 1024;
+  if (dp.stage_x) smem += xbytes;
   auto kern = gmres_dist_kernel<T>;
   LXB_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int occ = 0, dev = 0, sms = 0;
-  LXB_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kGridThreads, smem));
+  LXB_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kDistThreads, smem));
   LXB_CUDA_TRY(cudaGetDevice(&dev));
   LXB_CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
   if (occ < 1) return LXB_E_UNSUPPORTED;
   int nb = occ * sms;
   if (nb > grid_blocks()) nb = grid_blocks();
   void* args[] = {&dp};
-  LXB_CUDA_TRY(cudaLaunchCooperativeKernel((const void*)kern, dim3(nb), dim3(kGridThreads), args, smem, st));
+  LXB_CUDA_TRY(cudaLaunchCooperativeKernel((const void*)kern, dim3(nb), dim3(kDistThreads), args, smem, st));
   count_launch();
   return 0;
 }

@@ -97,10 +97,26 @@ struct GridTeam {
 
 // y[lo:hi) = scale * A[lo:hi, :] x, A streamed (no L1 allocation), x through L1/L2.
 // Ends with __syncthreads().
+// When `xs` (shared memory, >= n elements, 16-byte aligned) is given, x is first staged into it
+// (one coalesced pass per CTA) and the row dots read it from shared memory: independent of how
+// the memory x lives in is cached (peer-mapped symmetric buffers bypass L1).
 template <typename T>
 __device__ __forceinline__ void grid_matvec(const T* __restrict__ A, int n, int lo, int hi,
-                                            const T* __restrict__ x, T* __restrict__ y, T scale) {
+                                            const T* __restrict__ x, T* __restrict__ y, T scale,
+                                            T* xs = nullptr) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  if (xs != nullptr) {
+    if ((n % (16 / (int)sizeof(T)) == 0) && ((reinterpret_cast<uintptr_t>(x) & 15) == 0)) {
+      using VTs = typename V16K<T>::type;
+      const int nvs = n / (16 / (int)sizeof(T));
+      for (int c = threadIdx.x; c < nvs; c += blockDim.x)
+        reinterpret_cast<VTs*>(xs)[c] = __ldcg(reinterpret_cast<const VTs*>(x) + c);
+    } else {
+      for (int c = threadIdx.x; c < n; c += blockDim.x) xs[c] = __ldcg(x + c);
+    }
+    __syncthreads();
+    x = xs;
+  }
   constexpr int V = 16 / sizeof(T);
   constexpr int RB = 4;
   using VT = typename V16K<T>::type;
