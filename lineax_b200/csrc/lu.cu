@@ -12,6 +12,8 @@
 //   rows in LAPACK's physical row order (isamax), r = 1/pivot, l_ik = a_ik * r,
 //   a_ij = fma(-l_ik, u_kj, a_ij) for k ascending; solves use y_i = fma(-l_ik, y_k, y_i)
 //   and x_k = y_k * (1/u_kk), x_i = fma(-u_ik, x_k, x_i).
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace lxb {
@@ -169,8 +171,8 @@ __device__ __forceinline__ T lu_backsolve(const T (&a)[NP], T bb, int pos, T rdi
 }
 
 // MODE: 0 = factor only, 1 = factor + solve (lu/piv optional)
-template <typename T, int NP, bool SOLVE, bool FULL>
-__global__ void __launch_bounds__(kLuWarps * 32, (sizeof(T) == 4 && NP == 32) ? 3 : 1)
+template <typename T, int NP, bool SOLVE, bool FULL, int MINB = ((sizeof(T) == 4 && NP == 32) ? 3 : 1)>
+__global__ void __launch_bounds__(kLuWarps * 32, MINB)
     lu_warp_kernel(const T* __restrict__ A, int64_t sA, const T* __restrict__ B, int64_t sB,
                    T* __restrict__ X, T* __restrict__ LU, int32_t* __restrict__ PIV, int64_t batch,
                    int n, int fast) {
@@ -516,6 +518,11 @@ int launch_lu_warp_impl(const T* A, int64_t sA, const T* b, int64_t sb, T* x, T*
                         int64_t batch, int n, cudaStream_t st) {
   const size_t smem = (size_t)kLuWarps * (NP * NP + 2 * NP) * sizeof(T);
   auto kern = lu_warp_kernel<T, NP, SOLVE, FULL>;
+  if constexpr (sizeof(T) == 4 && NP == 32 && SOLVE && FULL) {
+    const char* e = getenv("LXB_LU_MINB");  // tuning knob: resident CTAs per SM the compiler targets
+    if (e && atoi(e) == 4) kern = lu_warp_kernel<T, NP, SOLVE, FULL, 4>;
+    if (e && atoi(e) == 2) kern = lu_warp_kernel<T, NP, SOLVE, FULL, 2>;
+  }
   LXB_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int fast = (n == NP) && aligned16(A) && ((sA * sizeof(T)) % 16 == 0) &&
                    (lu == nullptr || aligned16(lu));
