@@ -29,8 +29,9 @@ WORKLOADS = {
     "cg256": dict(batch=4096, n=256, desc="vmapped lx.CG on 4096 independent 256x256 SPD fp32 systems, rtol=atol=1e-6"),
     "gmres32k": dict(batch=1, n=32768, desc="lx.GMRES restart=20 on a 32768x32768 nonsymmetric fp32 dense system, rtol=atol=1e-6"),
     "lsmr262k": dict(batch=1, n=4096, m=262144, desc="lx.LSMR least squares on a 262144x4096 tall fp32 matrix, rtol=atol=1e-6"),
+    "qr262k": dict(batch=1, n=4096, m=262144, desc="lx.QR least squares (geqrf + ormqr + trtrs) on a 262144x4096 tall fp32 matrix"),
 }
-LARGE = ("gmres32k", "lsmr262k")
+LARGE = ("gmres32k", "lsmr262k", "qr262k")
 
 
 def measured_peaks():
@@ -200,6 +201,19 @@ def run_large(args, w, rank, local_rank, world):
         solve = lambda: _ops.gmres(A, b, None, None, 1e-6, 1e-6, 10 * n, 20, 20, 0)
         n_mv = lambda k: 1 + 21 * (k - 1)
         kernel_name = "gmres_grid_kernel<float>"
+    elif args.workload == "qr262k":
+        A = torch.randn(m, n, generator=g, device="cuda", dtype=torch.float32) / (m ** 0.5)
+        xt = torch.randn(n, generator=g, device="cuda", dtype=torch.float32)
+        b = _ops.matvec(A, xt, False) + 0.1 * torch.randn(m, generator=g, device="cuda", dtype=torch.float32)
+
+        def solve():
+            aq, taus = _ops.qr_factor(A)
+            x = _ops.qr_solve(aq, taus, b, False)
+            z = torch.zeros(1, dtype=torch.int32, device="cuda")
+            return x, z, z + 1
+
+        n_mv = lambda k: 0
+        kernel_name = "qr_panel_kernel + qr_wpartial_kernel + qr_update_kernel (blocked Householder)"
     else:
         A = torch.randn(m, n, generator=g, device="cuda", dtype=torch.float32) / (m ** 0.5)
         xt = torch.randn(n, generator=g, device="cuda", dtype=torch.float32)
@@ -248,7 +262,10 @@ def run_large(args, w, rank, local_rank, world):
     e2e_steps = 2
     for _ in range(e2e_steps):
         Ad, bd = a_pin.cuda(non_blocking=True), b_pin.cuda(non_blocking=True)
-        if sharded:
+        if args.workload == "qr262k":
+            aq_, t_ = _ops.qr_factor(Ad)
+            xo = _ops.qr_solve(aq_, t_, bd, False).cpu()
+        elif sharded:
             xo = solver.solve(Ad, bd)[0].cpu()
         elif args.workload == "gmres32k":
             xo = _ops.gmres(Ad, bd, None, None, 1e-6, 1e-6, 10 * n, 20, 20, 0)[0].cpu()
@@ -274,9 +291,17 @@ def run_large(args, w, rank, local_rank, world):
         "e2e": {"value": (1 if sharded else world) * e2e_steps / dt, "unit": "solves/s", "h2d_bytes_per_step": int(A.numel() * 4 + b.numel() * 4),
                 "d2h_bytes_per_step": int(n * 4), "steps": e2e_steps, "api": "lineax_b200._ops (host pinned -> device -> host)"},
         "gpu_launches": int(launches),
-        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": None, "kernel": kernel_name, "peak_source": peak_src,
-                     "algorithmic_bytes_per_launch": alg_bytes, "avg_launch_ms": ms / args.steps},
+        "roofline": ({"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                      "traffic": None, "kernel": kernel_name, "peak_source": peak_src,
+                      "algorithmic_bytes_per_launch": alg_bytes, "avg_launch_ms": ms / args.steps}
+                     if args.workload != "qr262k" else
+                     {"bound": "fp32_fma", "achieved": (2.0 * m * n * n - 2.0 / 3.0 * n ** 3 + 4.0 * m * n) / (ms / args.steps * 1e-3) / 1e12,
+                      "peak": 2 * 148 * 128 * 1.965e9 / 1e12, "unit": "TFLOP/s",
+                      "frac": (2.0 * m * n * n - 2.0 / 3.0 * n ** 3 + 4.0 * m * n) / (ms / args.steps * 1e-3) / (2 * 148 * 128 * 1.965e9),
+                      "traffic": None, "kernel": kernel_name,
+                      "peak_source": "nominal fp32 FMA peak 148 SMs x 128 lanes x 2 x 1.965 GHz (not in MEASURED_PEAKS.json)",
+                      "algorithmic_flops_per_step": 2.0 * m * n * n - 2.0 / 3.0 * n ** 3 + 4.0 * m * n,
+                      "avg_launch_ms": ms / args.steps}),
         "cpu_baseline": None,
     }
     print(json.dumps(line))

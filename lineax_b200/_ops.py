@@ -438,8 +438,9 @@ def _qr_factor(a: Tensor) -> Tuple[Tensor, Tensor]:
         a_ = a.contiguous()
         out = torch.empty(full + (rows, cols), dtype=a.dtype, device=a.device)
         taus = torch.empty(full + (cols,), dtype=a.dtype, device=a.device)
+        ws, ws_bytes = _workspace(f"lxb_qr_factor_workspace_{sfx}", a.device, math.prod(full), m, n)
         nat.call(f"lxb_qr_factor_{sfx}", a_.data_ptr(), m * n, out.data_ptr(), taus.data_ptr(),
-                 math.prod(full), m, n, None, 0, _stream())
+                 math.prod(full), m, n, _ptr(ws), ws_bytes, _stream())
     return out, taus
 
 
@@ -453,8 +454,10 @@ def _qr_solve(a: Tensor, taus: Tensor, b: Tensor, trans: bool) -> Tensor:
         t_, s_t = _operand(taus, 1, full)
         b_, s_b = _operand(b.to(a.dtype), 1, full)
         x = torch.empty(full + ((rows if trans else cols),), dtype=a.dtype, device=a.device)
+        ws, ws_bytes = _workspace(f"lxb_qr_solve_workspace_{sfx}", a.device, math.prod(full), rows, cols)
         nat.call(f"lxb_qr_solve_{sfx}", a_.data_ptr(), s_a, t_.data_ptr(), s_t, b_.data_ptr(), s_b,
-                 x.data_ptr(), math.prod(full), rows, cols, nat.TRANS if trans else 0, None, 0, _stream())
+                 x.data_ptr(), math.prod(full), rows, cols, nat.TRANS if trans else 0, _ptr(ws), ws_bytes,
+                 _stream())
     return x
 
 

@@ -286,6 +286,18 @@ __global__ void __launch_bounds__(kDirectThreads)
   }
 }
 
+// large single tall matrix: blocked Householder on all SMs (qr_large.cu)
+inline bool qr_use_large(int64_t batch, int rows, int cols) {
+  return batch == 1 && rows >= 4096 && cols >= 64 && (int64_t)rows * cols >= (int64_t)1 << 22;
+}
+template <typename T>
+int qr_large_factor(const T* A, T* a, T* taus, int m, int n, void* ws, size_t ws_bytes, cudaStream_t st);
+template <typename T>
+int qr_large_solve(const T* a, const T* taus, const T* b, T* x, int m, int n, void* ws, size_t ws_bytes,
+                   cudaStream_t st);
+template <typename T>
+size_t qr_large_ws_bytes(int m, int n);
+
 inline int64_t grid_for(int64_t batch, int occ) {
   const int64_t cap = (int64_t)kNumSMs * (occ < 1 ? 1 : occ);
   return batch < cap ? batch : cap;
@@ -355,10 +367,12 @@ int diagonal_solve(const T* d, int64_t sd, const T* b, int64_t sb, T* x, int64_t
 }
 
 template <typename T>
-int qr_factor(const T* A, int64_t sA, T* a, T* taus, int64_t batch, int m, int n, cudaStream_t st) {
+int qr_factor(const T* A, int64_t sA, T* a, T* taus, int64_t batch, int m, int n, void* ws, size_t ws_bytes,
+              cudaStream_t st) {
   if (batch < 0 || m < 0 || n < 0 || !A || !a || !taus) return LXB_E_BADARG;
   if (batch == 0 || m == 0 || n == 0) return 0;
   const int rows = m > n ? m : n, cols = m > n ? n : m;
+  if (m >= n && qr_use_large(batch, rows, cols)) return qr_large_factor<T>(A, a, taus, m, n, ws, ws_bytes, st);
   const size_t fixed = (32 + 8 * 33 + ((cols + 3) & ~3)) * sizeof(T);
   if (fixed > kMaxSmemD) return LXB_E_UNSUPPORTED;
   const size_t mat = (size_t)rows * (cols + 1) * sizeof(T);
@@ -374,9 +388,11 @@ int qr_factor(const T* A, int64_t sA, T* a, T* taus, int64_t batch, int m, int n
 
 template <typename T>
 int qr_solve(const T* a, int64_t sa, const T* taus, int64_t stau, const T* b, int64_t sb, T* x,
-             int64_t batch, int rows, int cols, int flags, cudaStream_t st) {
+             int64_t batch, int rows, int cols, int flags, void* ws, size_t ws_bytes, cudaStream_t st) {
   if (batch < 0 || rows < 0 || cols < 0 || !a || !taus || !b || !x) return LXB_E_BADARG;
   if (batch == 0 || rows == 0 || cols == 0) return 0;
+  if (!(flags & LXB_TRANS) && qr_use_large(batch, rows, cols))
+    return qr_large_solve<T>(a, taus, b, x, rows, cols, ws, ws_bytes, st);
   const size_t smem = (32 + (size_t)rows) * sizeof(T);
   if (smem > kMaxSmemD) return LXB_E_UNSUPPORTED;
   int occ = 1, rc = occupancy(qr_solve_kernel<T>, kDirectThreads, smem, &occ);
@@ -415,26 +431,21 @@ int qr_solve(const T* a, int64_t sa, const T* taus, int64_t stau, const T* b, in
   extern "C" int lxb_qr_factor_##sfx(const T* A, int64_t stride_A, T* a, T* taus, int64_t batch,   \
                                      int32_t m, int32_t n, void* workspace,                        \
                                      size_t workspace_bytes, lxb_stream_t stream) {                \
-    (void)workspace;                                                                               \
-    (void)workspace_bytes;                                                                         \
-    return lxb::qr_factor<T>(A, stride_A, a, taus, batch, m, n, (cudaStream_t)stream);             \
+    return lxb::qr_factor<T>(A, stride_A, a, taus, batch, m, n, workspace, workspace_bytes,        \
+                             (cudaStream_t)stream);                                                \
   }                                                                                                \
   extern "C" size_t lxb_qr_factor_workspace_##sfx(int64_t batch, int32_t m, int32_t n) {           \
-    (void)batch; (void)m; (void)n;                                                                 \
-    return 0;                                                                                      \
+    return (m >= n && lxb::qr_use_large(batch, m, n)) ? lxb::qr_large_ws_bytes<T>(m, n) : 0;       \
   }                                                                                                \
   extern "C" int lxb_qr_solve_##sfx(const T* a, int64_t stride_a, const T* taus, int64_t stride_t, \
                                     const T* b, int64_t stride_b, T* x, int64_t batch,             \
                                     int32_t rows, int32_t cols, int32_t flags, void* workspace,    \
                                     size_t workspace_bytes, lxb_stream_t stream) {                 \
-    (void)workspace;                                                                               \
-    (void)workspace_bytes;                                                                         \
     return lxb::qr_solve<T>(a, stride_a, taus, stride_t, b, stride_b, x, batch, rows, cols, flags, \
-                            (cudaStream_t)stream);                                                 \
+                            workspace, workspace_bytes, (cudaStream_t)stream);                     \
   }                                                                                                \
   extern "C" size_t lxb_qr_solve_workspace_##sfx(int64_t batch, int32_t rows, int32_t cols) {      \
-    (void)batch; (void)rows; (void)cols;                                                           \
-    return 0;                                                                                      \
+    return lxb::qr_use_large(batch, rows, cols) ? lxb::qr_large_ws_bytes<T>(rows, cols) : 0;       \
   }
 LXB_DEF_DIRECT(f32, float)
 LXB_DEF_DIRECT(f64, double)

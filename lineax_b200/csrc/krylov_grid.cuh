@@ -14,7 +14,7 @@ namespace lxb {
 namespace cgx = cooperative_groups;
 
 constexpr int kGridThreads = 256;
-constexpr int kGridMaxK = 40;  // widest reduction (GMRES restart + 1 <= 40 in grid mode)
+constexpr int kGridMaxK = 72;  // widest reduction: QR panel (64), GMRES restart + 2 <= 72
 
 template <typename T>
 struct GridTeam {

@@ -6,7 +6,7 @@ namespace lxb {
 
 constexpr int kGridCtasPerSm = 2;
 inline int grid_blocks() { return kNumSMs * kGridCtasPerSm; }
-constexpr int kGridMaxKHost = 40;
+constexpr int kGridMaxKHost = 72;
 __host__ __device__ inline size_t grid_part_elems() {
   // 2 reduction buffers x kGridMaxK x nb, padded to a multiple of 4 elements
   return ((size_t)2 * kGridMaxKHost * kNumSMs * kGridCtasPerSm + 3) & ~(size_t)3;

@@ -137,3 +137,25 @@ def test_diagonal_and_triangular(dtype):
                     for i in range(3):
                         xr = oracle.triangular_compute(a[i], bb[i], lower, unit, int(trans))
                         assert_close(x[i], xr, dtype, factor=1e4)
+
+
+@pytest.mark.parametrize("shape,dtype", [((4096, 256), np.float32), ((8192, 130), np.float64),
+                                          ((20000, 96), np.float32), ((65536, 64), np.float32)])
+def test_qr_large_blocked(shape, dtype):
+    """Blocked (compact WY) Householder QR on all SMs for one large tall matrix: same R / taus as
+    LAPACK geqrf (identical sign conventions) and the least-squares solution of qr.py:89-92."""
+    m, n = shape
+    a, b, _ = gen.tall_lstsq(m + n, m, n, dtype)
+    aq, taus = _ops().qr_factor(dev(a[None]))
+    x = host(_ops().qr_solve(aq, taus, dev(b[None]), False))[0]
+    (a_ref, taus_ref), _ = oracle.qr_init(a)
+    tolf = 2e-3 if dtype == np.float32 else 1e-9
+    r_gpu, r_ref = np.triu(host(aq)[0][:n]), np.triu(a_ref[:n])
+    assert np.max(np.abs(r_gpu - r_ref)) <= tolf * np.max(np.abs(r_ref))
+    assert np.max(np.abs(host(taus)[0] - taus_ref)) <= tolf
+    v_gpu, v_ref = np.tril(host(aq)[0], -1), np.tril(a_ref, -1)
+    assert np.max(np.abs(v_gpu - v_ref)) <= 10 * tolf * max(1.0, np.max(np.abs(v_ref)))
+    xl = np.linalg.lstsq(a.astype(np.float64), b.astype(np.float64), rcond=None)[0]
+    assert np.max(np.abs(x - xl)) / np.abs(xl).max() < (5e-4 if dtype == np.float32 else 1e-9)
+    xr = oracle.qr_compute(oracle.qr_init(a), b)
+    assert_close(x, xr, dtype, factor=2000)
