@@ -58,9 +58,19 @@ __global__ void __launch_bounds__(kGridThreads)
   for (int jj = 0; jj < nbw; ++jj) {
     const int jrow = jj;  // local (panel) row index of the diagonal element: global row j0 + jj
     // Gram row over own rows strictly below the diagonal + the pivot row itself
+    // 8 rows in flight per warp: the panel is L2-resident in global mode, so the loads must overlap
     T acc = T(0);
-    for (int r = warp; r < nrows; r += nw) {
-      if (lo + r > jrow && cok) acc = fma_(P[r * ldp + jj], P[r * ldp + lane], acc);
+    for (int r0 = warp; r0 < nrows; r0 += 8 * nw) {
+      T pj[8], pc[8];
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        const int r = r0 + q * nw;
+        const bool ok = r < nrows && lo + r > jrow && cok;
+        pj[q] = ok ? P[r * ldp + jj] : T(0);
+        pc[q] = ok ? P[r * ldp + lane] : T(0);
+      }
+#pragma unroll
+      for (int q = 0; q < 8; ++q) acc = fma_(pj[q], pc[q], acc);
     }
     wsum[warp * 32 + lane] = acc;
     __syncthreads();
@@ -85,16 +95,30 @@ __global__ void __launch_bounds__(kGridThreads)
     if (tid < 32) fc[tid] = tid > jj && tid < nbw ? tau * (vals[32 + tid] + scal * vals[tid]) : T(0);
     __syncthreads();
     // v = scal * a[:, jj] below the diagonal; trailing panel columns -= f_c v
-    for (int r = warp; r < nrows; r += nw) {
-      const int lr = lo + r;
-      if (lr > jrow) {
-        const T v = P[r * ldp + jj] * scal;
-        __syncwarp();
-        if (lane == jj) P[r * ldp + jj] = v;
-        else if (lane > jj && cok) P[r * ldp + lane] = fma_(-fc[lane], v, P[r * ldp + lane]);
-      } else if (lr == jrow) {
-        if (lane == jj) P[r * ldp + jj] = beta;
-        else if (lane > jj && cok) P[r * ldp + lane] = P[r * ldp + lane] - fc[lane];
+    const T fcl = fc[lane];
+    for (int r0 = warp; r0 < nrows; r0 += 8 * nw) {
+      T pj[8], pc[8];
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        const int r = r0 + q * nw;
+        const bool ok = r < nrows && lo + r >= jrow && cok;
+        pj[q] = ok ? P[r * ldp + jj] : T(0);
+        pc[q] = ok ? P[r * ldp + lane] : T(0);
+      }
+      __syncwarp();
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        const int r = r0 + q * nw;
+        if (r >= nrows || !cok) continue;
+        const int lr = lo + r;
+        if (lr > jrow) {
+          const T v = pj[q] * scal;
+          if (lane == jj) P[r * ldp + jj] = v;
+          else if (lane > jj) P[r * ldp + lane] = fma_(-fcl, v, pc[q]);
+        } else if (lr == jrow) {
+          if (lane == jj) P[r * ldp + jj] = beta;
+          else if (lane > jj) P[r * ldp + lane] = pc[q] - fcl;
+        }
       }
     }
     if (team.bid == 0 && tid == 0) taus[j0 + jj] = tau;
@@ -109,14 +133,30 @@ __global__ void __launch_bounds__(kGridThreads)
     }
   }
   // Gram of V (unit lower trapezoidal): G[c1][c2] = sum_i v(i,c1) v(i,c2), per-CTA partial -> global
-  for (int c1 = warp; c1 < kPB; c1 += nw) {
-    T acc = T(0);
-    for (int r = 0; r < nrows; ++r) {
+  // warps split the rows (each row is read once as a coalesced 128-byte line and kept in a register
+  // per lane); lane = column c2; the 32 columns c1 are broadcast with shuffles
+  {
+    T g[kPB];
+#pragma unroll
+    for (int c1 = 0; c1 < kPB; ++c1) g[c1] = T(0);
+    for (int r = warp; r < nrows; r += nw) {
       const int gr = j0 + lo + r;
-      if (cok && c1 < nbw)
-        acc = fma_(vmask<T>(P[r * ldp + c1], gr, j0, c1), vmask<T>(P[r * ldp + lane], gr, j0, lane), acc);
+      const T mine = cok ? vmask<T>(P[r * ldp + lane], gr, j0, lane) : T(0);
+#pragma unroll
+      for (int c1 = 0; c1 < kPB; ++c1) g[c1] = fma_(__shfl_sync(kFull, mine, c1), mine, g[c1]);
     }
-    gpart[(size_t)team.bid * (kPB * kPB) + c1 * kPB + lane] = acc;
+    // cross-warp sum through shared memory (Gs reused as scratch: 8 warps x 32 x 32 does not fit,
+    // so accumulate warp by warp)
+    for (int e = tid; e < kPB * kPB; e += nt) Gs[e] = T(0);
+    __syncthreads();
+    for (int w = 0; w < nw; ++w) {
+      if (warp == w) {
+#pragma unroll
+        for (int c1 = 0; c1 < kPB; ++c1) Gs[c1 * kPB + lane] += g[c1];
+      }
+      __syncthreads();
+    }
+    for (int e = tid; e < kPB * kPB; e += nt) gpart[(size_t)team.bid * (kPB * kPB) + e] = Gs[e];
   }
   __threadfence();
   team.sync();
@@ -147,49 +187,69 @@ __global__ void __launch_bounds__(kGridThreads)
 }
 
 // ------------------------------------------------------------- K2: W partial ----
-// Wp[g][k][c] = sum_{i in row group g} v(i,k) * A[i][cbase + c]; tile = 128 columns.
+// Wp[g][k][c] = sum_{i in row group g} v(i,k) * A[i][cbase + c]; CTA tile = 32 k x 256 columns,
+// thread tile 4 k x 8 columns (32 FMA per 3 LDS.128); the next 32-row chunk is prefetched from
+// global memory into registers while the current one is consumed from shared memory.
+constexpr int kW2Tile = 256;
 template <typename T>
 __global__ void __launch_bounds__(256)
     qr_wpartial_kernel(const T* __restrict__ a, T* __restrict__ Wp, int m, int n, int j0, int ncols,
                        int ngroups) {
-  __shared__ __align__(16) T Vs[32][kPB];
-  __shared__ __align__(16) T As[32][128];
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  T(*Vs)[kPB] = reinterpret_cast<T(*)[kPB]>(smem_raw);                              // [32][32]
+  T(*As)[kW2Tile] = reinterpret_cast<T(*)[kW2Tile]>(smem_raw + 32 * kPB * sizeof(T));  // [32][256]
   const int tid = threadIdx.x;
   const int tile = blockIdx.x, grp = blockIdx.y;
-  const int cbase = j0 + kPB + tile * 128;       // global column of the tile start
-  const int cw = min(128, j0 + kPB + ncols - cbase);
+  const int cbase = j0 + kPB + tile * kW2Tile;
+  const int cw = min(kW2Tile, j0 + kPB + ncols - cbase);
   const int rows_total = m - j0;
   const int per = (((rows_total + ngroups - 1) / ngroups) + 31) & ~31;
   const int r0 = j0 + grp * per, r1 = min(m, r0 + per);
-  const int kq = tid >> 5, cq = tid & 31;        // 8 groups of 4 k's, 32 groups of 4 columns
-  T acc[4][4];
+  const int kq = tid >> 5, cq = tid & 31;  // 8 groups of 4 k's, 32 groups of 8 columns
+  T acc[4][8];
 #pragma unroll
   for (int x = 0; x < 4; ++x)
 #pragma unroll
-    for (int y = 0; y < 4; ++y) acc[x][y] = T(0);
-  for (int rb = r0; rb < r1; rb += 32) {
-    // stage 32 rows of V (masked) and of the A tile
-    for (int idx = tid; idx < 32 * kPB; idx += 256) {
-      const int r = idx / kPB, c = idx % kPB, gr = rb + r;
-      Vs[r][c] = gr < r1 ? vmask<T>(a[(size_t)gr * n + j0 + c], gr, j0, c) : T(0);
+    for (int y = 0; y < 8; ++y) acc[x][y] = T(0);
+  // staging assignment: V chunk 32x32 -> 4 elements per thread; A chunk 32x256 -> 32 per thread
+  T pv[4], pa[32];
+  auto fetch = [&](int rb) {
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int idx = tid + q * 256, r = idx / kPB, c = idx % kPB, gr = rb + r;
+      pv[q] = gr < r1 ? vmask<T>(a[(size_t)gr * n + j0 + c], gr, j0, c) : T(0);
     }
-    for (int idx = tid; idx < 32 * 128; idx += 256) {
-      const int r = idx / 128, c = idx % 128, gr = rb + r;
-      As[r][c] = (gr < r1 && c < cw) ? a[(size_t)gr * n + cbase + c] : T(0);
+#pragma unroll
+    for (int q = 0; q < 32; ++q) {
+      const int idx = tid + q * 256, r = idx / kW2Tile, c = idx % kW2Tile, gr = rb + r;
+      pa[q] = (gr < r1 && c < cw) ? a[(size_t)gr * n + cbase + c] : T(0);
+    }
+  };
+  if (r0 < r1) fetch(r0);
+  for (int rb = r0; rb < r1; rb += 32) {
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int idx = tid + q * 256;
+      Vs[idx / kPB][idx % kPB] = pv[q];
+    }
+#pragma unroll
+    for (int q = 0; q < 32; ++q) {
+      const int idx = tid + q * 256;
+      As[idx / kW2Tile][idx % kW2Tile] = pa[q];
     }
     __syncthreads();
-#pragma unroll 8
+    if (rb + 32 < r1) fetch(rb + 32);
+#pragma unroll 4
     for (int r = 0; r < 32; ++r) {
-      T v[4], x[4];
+      T v[4], x[8];
 #pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        v[e] = Vs[r][4 * kq + e];
-        x[e] = As[r][4 * cq + e];
-      }
+      for (int e = 0; e < 4; ++e) v[e] = Vs[r][4 * kq + e];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) x[e] = As[r][8 * cq + e];
 #pragma unroll
       for (int p = 0; p < 4; ++p)
 #pragma unroll
-        for (int q = 0; q < 4; ++q) acc[p][q] = fma_(v[p], x[q], acc[p][q]);
+        for (int q = 0; q < 8; ++q) acc[p][q] = fma_(v[p], x[q], acc[p][q]);
     }
     __syncthreads();
   }
@@ -197,8 +257,8 @@ __global__ void __launch_bounds__(256)
 #pragma unroll
   for (int p = 0; p < 4; ++p)
 #pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      const int c = tile * 128 + 4 * cq + q;
+    for (int q = 0; q < 8; ++q) {
+      const int c = tile * kW2Tile + 8 * cq + q;
       if (c < ncols) out[(size_t)(4 * kq + p) * ncols + c] = acc[p][q];
     }
 }
@@ -269,16 +329,29 @@ __global__ void __launch_bounds__(256)
 #pragma unroll
       for (int q = 0; q < 8; ++q) acc[p][q] = fma_(v[p], w[q], acc[p][q]);
   }
+  using VT = typename V16K<T>::type;
+  constexpr int V = 16 / sizeof(T);
+  const bool vec = (n % V == 0) && ((reinterpret_cast<uintptr_t>(a) & 15) == 0) &&
+                   (tile * 128 + 8 * ci + 8 <= ncols);
 #pragma unroll
   for (int p = 0; p < 4; ++p) {
     const int gr = rb + 4 * ri + p;
     if (gr >= m) continue;
+    T* rowp = a + (size_t)gr * n + cbase + 8 * ci;
+    if (vec) {
 #pragma unroll
-    for (int q = 0; q < 8; ++q) {
-      const int gc = tile * 128 + 8 * ci + q;
-      if (gc < ncols) {
-        T* ptr = a + (size_t)gr * n + cbase + 8 * ci + q;
-        *ptr = *ptr - acc[p][q];
+      for (int h = 0; h < 8 / V; ++h) {
+        VT val = reinterpret_cast<VT*>(rowp)[h];
+        T* pv = reinterpret_cast<T*>(&val);
+#pragma unroll
+        for (int e = 0; e < V; ++e) pv[e] = pv[e] - acc[p][h * V + e];
+        reinterpret_cast<VT*>(rowp)[h] = val;
+      }
+    } else {
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        const int gc = tile * 128 + 8 * ci + q;
+        if (gc < ncols) rowp[q] = rowp[q] - acc[p][q];
       }
     }
   }
@@ -370,7 +443,7 @@ QrLargePlan<T> qr_large_plan(int m, int n) {
   pl.in_smem = (fixed_panel + rows_bytes) * kGridCtasPerSm <= 220 * 1024;
   pl.smem_panel = fixed_panel + (pl.in_smem ? rows_bytes : 0);
   pl.smem_apply = fixed_apply + (pl.in_smem ? rows_bytes : 0);
-  pl.ngroups = 16;
+  pl.ngroups = 32;
   size_t off = grid_part_elems();
   pl.gpart_off = off; off += (size_t)pl.nb * kPB * kPB;
   pl.t_off = off; off += kPB * kPB;
@@ -410,8 +483,11 @@ int qr_large_factor(const T* A, T* a, T* taus, int m, int n, void* ws, size_t ws
     const int ncols = n - j0 - kPB;
     if (ncols <= 0) break;
     const int tiles = (ncols + 127) / 128;
+    const int wtiles = (ncols + kW2Tile - 1) / kW2Tile;
     int ngroups = pl.ngroups;
-    qr_wpartial_kernel<T><<<dim3(tiles, ngroups), 256, 0, st>>>(a, Wp, m, n, j0, ncols, ngroups);
+    const size_t w_smem = (size_t)(32 * kPB + 32 * kW2Tile) * sizeof(T);
+    LXB_CUDA_TRY(cudaFuncSetAttribute(qr_wpartial_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)w_smem));
+    qr_wpartial_kernel<T><<<dim3(wtiles, ngroups), 256, w_smem, st>>>(a, Wp, m, n, j0, ncols, ngroups);
     LXB_CUDA_CHECK_LAUNCH();
     qr_wfinish_kernel<T><<<(ncols + 255) / 256, 256, 0, st>>>(Wp, Tm, W2, ncols, ngroups);
     LXB_CUDA_CHECK_LAUNCH();
