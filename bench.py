@@ -30,8 +30,9 @@ WORKLOADS = {
     "gmres32k": dict(batch=1, n=32768, desc="lx.GMRES restart=20 on a 32768x32768 nonsymmetric fp32 dense system, rtol=atol=1e-6"),
     "lsmr262k": dict(batch=1, n=4096, m=262144, desc="lx.LSMR least squares on a 262144x4096 tall fp32 matrix, rtol=atol=1e-6"),
     "qr262k": dict(batch=1, n=4096, m=262144, desc="lx.QR least squares (geqrf + ormqr + trtrs) on a 262144x4096 tall fp32 matrix"),
+    "tridiag512": dict(batch=1 << 20, n=512, desc="vmapped lx.Tridiagonal on 2^20 independent systems of length 512, fp32"),
 }
-LARGE = ("gmres32k", "lsmr262k", "qr262k")
+LARGE = ("gmres32k", "lsmr262k", "qr262k", "tridiag512")
 
 
 def measured_peaks():
@@ -201,6 +202,24 @@ def run_large(args, w, rank, local_rank, world):
         solve = lambda: _ops.gmres(A, b, None, None, 1e-6, 1e-6, 10 * n, 20, 20, 0)
         n_mv = lambda k: 1 + 21 * (k - 1)
         kernel_name = "gmres_grid_kernel<float>"
+    elif args.workload == "tridiag512":
+        # strictly diagonally dominant, d = 4 + |N|, |l| + |u| < |d|
+        B_ = w["batch"]
+        d_ = 4.0 + torch.randn(B_, n, generator=g, device="cuda").abs()
+        l_ = torch.randn(B_, n - 1, generator=g, device="cuda").clamp(-1.9, 1.9)
+        u_ = torch.randn(B_, n - 1, generator=g, device="cuda").clamp(-1.9, 1.9)
+        b = torch.randn(B_, n, generator=g, device="cuda")
+        A = d_
+        xt = None
+        m = B_
+
+        def solve():
+            x = _ops.tridiagonal_solve(d_, l_, u_, b)
+            z = torch.zeros(1, dtype=torch.int32, device="cuda")
+            return x, z, z + 1
+
+        n_mv = lambda k: 0
+        kernel_name = "tridiagonal_kernel<float>"
     elif args.workload == "qr262k":
         A = torch.randn(m, n, generator=g, device="cuda", dtype=torch.float32) / (m ** 0.5)
         xt = torch.randn(n, generator=g, device="cuda", dtype=torch.float32)
@@ -256,8 +275,16 @@ def run_large(args, w, rank, local_rank, world):
     ms = float(t.item())
     k = int(out[2].item())
     res = int(out[1].item())
-    xerr = float((out[0] - xt).abs().max() / xt.abs().max())
-    alg_bytes = n_mv(k) * m * n * 4  # per GPU (m = local rows when row-sharded)
+    if args.workload == "tridiag512":
+        x_ = out[0]
+        rr = d_ * x_ - b
+        rr[:, :-1] += u_ * x_[:, 1:]
+        rr[:, 1:] += l_ * x_[:, :-1]
+        xerr = float(rr.abs().max())  # max residual
+        alg_bytes = 5 * m * n * 4    # 5 n s per solve
+    else:
+        xerr = float((out[0] - xt).abs().max() / xt.abs().max())
+        alg_bytes = n_mv(k) * m * n * 4  # per GPU (m = local rows when row-sharded)
     peak, peak_src = measured_peaks()
     traffic = None
     tp = os.path.join(ROOT, "profiles", "traffic.json")
@@ -267,12 +294,16 @@ def run_large(args, w, rank, local_rank, world):
     # e2e: host matrix -> device -> solve -> host solution, every step
     a_pin = A.cpu().pin_memory()
     b_pin = b.cpu().pin_memory()
+    if args.workload == "tridiag512":
+        l_pin, u_pin = l_.cpu().pin_memory(), u_.cpu().pin_memory()
     torch.cuda.synchronize()
     t0 = time.perf_counter()
     e2e_steps = 2
     for _ in range(e2e_steps):
         Ad, bd = a_pin.cuda(non_blocking=True), b_pin.cuda(non_blocking=True)
-        if args.workload == "qr262k":
+        if args.workload == "tridiag512":
+            xo = _ops.tridiagonal_solve(Ad, l_pin.cuda(non_blocking=True), u_pin.cuda(non_blocking=True), bd).cpu()
+        elif args.workload == "qr262k":
             aq_, t_ = _ops.qr_factor(Ad)
             xo = _ops.qr_solve(aq_, t_, bd, False).cpu()
         elif sharded:
@@ -288,7 +319,7 @@ def run_large(args, w, rank, local_rank, world):
         return
     line = {
         "metric": f"solves/sec ({w['desc']})",
-        "value": (1 if sharded else world) * args.steps / (ms * 1e-3), "unit": "solves/s",
+        "value": (1 if sharded else world) * w["batch"] * args.steps / (ms * 1e-3), "unit": "solves/s",
         "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
         "higher_is_better": True, "scaling": "strong" if sharded else "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
@@ -298,8 +329,9 @@ def run_large(args, w, rank, local_rank, world):
                                    else f"replica x{world}"),
                    "l2": "the 4.3 GB operator is far larger than the 126 MB L2"},
         "clocks": clocks,
-        "e2e": {"value": (1 if sharded else world) * e2e_steps / dt, "unit": "solves/s", "h2d_bytes_per_step": int(A.numel() * 4 + b.numel() * 4),
-                "d2h_bytes_per_step": int(n * 4), "steps": e2e_steps, "api": "lineax_b200._ops (host pinned -> device -> host)"},
+        "e2e": {"value": (1 if sharded else world) * w["batch"] * e2e_steps / dt, "unit": "solves/s",
+                "h2d_bytes_per_step": int(A.numel() * 4 + b.numel() * 4 + (2 * l_.numel() * 4 if args.workload == "tridiag512" else 0)),
+                "d2h_bytes_per_step": int(n * 4 * w["batch"]), "steps": e2e_steps, "api": "lineax_b200._ops (host pinned -> device -> host)"},
         "gpu_launches": int(launches),
         "roofline": ({"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                       "traffic": traffic, "kernel": kernel_name, "peak_source": peak_src,
