@@ -254,7 +254,8 @@ def run_large(args, w, rank, local_rank, world):
         sampler.start()
     t_soak = time.perf_counter()
     n_soak = 0
-    while time.perf_counter() - t_soak < 0.4 and n_soak < 50:  # clock samples under load (untimed)
+    soak_s = 0.0 if os.environ.get("LXB_NO_SOAK") == "1" else 0.4
+    while time.perf_counter() - t_soak < soak_s and n_soak < 50:  # clock samples under load (untimed)
         out = solve()
         torch.cuda.synchronize()
         n_soak += 1

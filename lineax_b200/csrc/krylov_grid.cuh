@@ -95,6 +95,64 @@ struct GridTeam {
   }
 };
 
+// RB rows per warp per sweep, UNR column chunks in flight per row: RB * UNR 128-bit loads per lane.
+template <typename T, int RB, int UNR>
+__device__ __forceinline__ void grid_matvec_rows(const T* __restrict__ A, int n, int lo, int hi,
+                                                 const T* __restrict__ x, T* __restrict__ y, T scale) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  constexpr int V = 16 / sizeof(T);
+  using VT = typename V16K<T>::type;
+  const VT* x4 = reinterpret_cast<const VT*>(x);
+  const int nv = n / V;
+  for (int i0 = lo + warp * RB; i0 < hi; i0 += nw * RB) {
+    T acc[RB];
+    const VT* rows[RB];
+#pragma unroll
+    for (int r = 0; r < RB; ++r) {
+      acc[r] = T(0);
+      const int i = i0 + r < hi ? i0 + r : hi - 1;
+      rows[r] = reinterpret_cast<const VT*>(A + (size_t)i * n);
+    }
+    // explicit UNR-way unroll: RB * UNR independent 128-bit loads are issued before any is used
+    int c = lane;
+    for (; c + 32 * (UNR - 1) < nv; c += 32 * UNR) {
+      VT a[UNR][RB], b[UNR];
+#pragma unroll
+      for (int u = 0; u < UNR; ++u) {
+#pragma unroll
+        for (int r = 0; r < RB; ++r) a[u][r] = ldg_stream(rows[r] + c + 32 * u);
+        b[u] = x4[c + 32 * u];
+      }
+#pragma unroll
+      for (int u = 0; u < UNR; ++u) {
+        const T* pb = reinterpret_cast<const T*>(&b[u]);
+#pragma unroll
+        for (int r = 0; r < RB; ++r) {
+          const T* pa = reinterpret_cast<const T*>(&a[u][r]);
+#pragma unroll
+          for (int e = 0; e < V; ++e) acc[r] = fma_(pa[e], pb[e], acc[r]);
+        }
+      }
+    }
+    for (; c < nv; c += 32) {
+      const VT b = x4[c];
+      const T* pb = reinterpret_cast<const T*>(&b);
+#pragma unroll
+      for (int r = 0; r < RB; ++r) {
+        const VT a = ldg_stream(rows[r] + c);
+        const T* pa = reinterpret_cast<const T*>(&a);
+#pragma unroll
+        for (int e = 0; e < V; ++e) acc[r] = fma_(pa[e], pb[e], acc[r]);
+      }
+    }
+#pragma unroll
+    for (int r = 0; r < RB; ++r) {
+      const T s = warp_sum(acc[r]);
+      if (lane == 0 && i0 + r < hi) y[i0 + r] = scale * s;
+    }
+  }
+}
+
 // y[lo:hi) = scale * A[lo:hi, :] x, A streamed (no L1 allocation), x through L1/L2.
 // Ends with __syncthreads().
 // When `xs` (shared memory, >= n elements, 16-byte aligned) is given, x is first staged into it
@@ -118,42 +176,14 @@ __device__ __forceinline__ void grid_matvec(const T* __restrict__ A, int n, int 
     x = xs;
   }
   constexpr int V = 16 / sizeof(T);
-  constexpr int RB = 4;
-  using VT = typename V16K<T>::type;
   const bool vec = (n % V == 0) && ((reinterpret_cast<uintptr_t>(A) & 15) == 0) &&
                    ((reinterpret_cast<uintptr_t>(x) & 15) == 0);
   if (vec) {
-    const VT* x4 = reinterpret_cast<const VT*>(x);
-    const int nv = n / V;
-    for (int i0 = lo + warp * RB; i0 < hi; i0 += nw * RB) {
-      T acc[RB];
-      const VT* rows[RB];
-#pragma unroll
-      for (int r = 0; r < RB; ++r) {
-        acc[r] = T(0);
-        const int i = i0 + r < hi ? i0 + r : hi - 1;
-        rows[r] = reinterpret_cast<const VT*>(A + (size_t)i * n);
-      }
-#pragma unroll 2
-      for (int c = lane; c < nv; c += 32) {
-        VT a[RB];
-#pragma unroll
-        for (int r = 0; r < RB; ++r) a[r] = ldg_stream(rows[r] + c);
-        const VT b = x4[c];
-        const T* pb = reinterpret_cast<const T*>(&b);
-#pragma unroll
-        for (int r = 0; r < RB; ++r) {
-          const T* pa = reinterpret_cast<const T*>(&a[r]);
-#pragma unroll
-          for (int e = 0; e < V; ++e) acc[r] = fma_(pa[e], pb[e], acc[r]);
-        }
-      }
-#pragma unroll
-      for (int r = 0; r < RB; ++r) {
-        const T s = warp_sum(acc[r]);
-        if (lane == 0 && i0 + r < hi) y[i0 + r] = scale * s;
-      }
-    }
+    // rows per warp per sweep: keep every warp busy when the CTA owns few rows (multi-GPU slices)
+    const int rows = hi - lo;
+    if (rows >= 4 * nw) grid_matvec_rows<T, 4, 2>(A, n, lo, hi, x, y, scale);
+    else if (rows >= 2 * nw) grid_matvec_rows<T, 2, 4>(A, n, lo, hi, x, y, scale);
+    else grid_matvec_rows<T, 1, 8>(A, n, lo, hi, x, y, scale);
   } else {
     for (int i = lo + warp; i < hi; i += nw) {
       const T s = row_dot<T, false>(A + (size_t)i * n, x, n, lane);
