@@ -69,17 +69,23 @@ __device__ __forceinline__ void stage_read_row(const T* stage, int row, T (&a)[N
   }
 }
 
-// Pick the pivot lane: max |a| over candidate lanes, ties -> smallest physical position.
-__device__ __forceinline__ int pick_pivot(float v, bool cand, int pos) {
+// Pivot choice: max |a| over candidate lanes, ties -> smallest physical position (LAPACK ISAMAX).
+// Returns a PREDICATE (am I the pivot lane) instead of a lane index: ncu showed the XU pipe
+// (FLO/BREV/POPC from __ffs/__popc, MUFU) at 79 % -- the real limiter of the first version -- so the
+// hot loop avoids index extraction altogether and broadcasts through shared memory.
+__device__ __forceinline__ bool pick_pivot(float v, bool cand, int pos) {
   // every NaN maps to one key so that, like ISAMAX, the first NaN wins
   const unsigned key = cand ? (v != v ? 0x7fc00000u : (__float_as_uint(v) & 0x7fffffffu)) + 1u : 0u;
   const unsigned m = __reduce_max_sync(kFull, key);
-  const unsigned tied = __ballot_sync(kFull, key == m);
-  if (__popc(tied) == 1) return __ffs(tied) - 1;
-  const int pm = __reduce_min_sync(kFull, key == m ? pos : 1 << 20);
-  return __ffs(__ballot_sync(kFull, key == m && pos == pm)) - 1;
+  bool is = key == m;
+  const unsigned tied = __ballot_sync(kFull, is);
+  if (tied & (tied - 1u)) {  // more than one candidate holds the maximum
+    const int pm = __reduce_min_sync(kFull, is ? pos : 1 << 20);
+    is = is && pos == pm;
+  }
+  return is;
 }
-__device__ __forceinline__ int pick_pivot(double v, bool cand, int pos) {
+__device__ __forceinline__ bool pick_pivot(double v, bool cand, int pos) {
   const unsigned long long key =
       cand ? (v != v ? 0x7ff8000000000000ull
                      : ((unsigned long long)__double_as_longlong(v) & 0x7fffffffffffffffull)) + 1ull
@@ -87,12 +93,21 @@ __device__ __forceinline__ int pick_pivot(double v, bool cand, int pos) {
   const unsigned hi = (unsigned)(key >> 32), lo = (unsigned)key;
   const unsigned mh = __reduce_max_sync(kFull, hi);
   const unsigned ml = __reduce_max_sync(kFull, hi == mh ? lo : 0u);
-  const bool is = hi == mh && lo == ml;
+  bool is = hi == mh && lo == ml;
   const unsigned tied = __ballot_sync(kFull, is);
-  if (__popc(tied) == 1) return __ffs(tied) - 1;
-  const int pm = __reduce_min_sync(kFull, is ? pos : 1 << 20);
-  return __ffs(__ballot_sync(kFull, is && pos == pm)) - 1;
+  if (tied & (tied - 1u)) {
+    const int pm = __reduce_min_sync(kFull, is ? pos : 1 << 20);
+    is = is && pos == pm;
+  }
+  return is;
 }
+
+__device__ __forceinline__ float int_as_T(int v, float) { return __int_as_float(v); }
+__device__ __forceinline__ double int_as_T(int v, double) { return __longlong_as_double((long long)v); }
+__device__ __forceinline__ int T_as_int(float v) { return __float_as_int(v); }
+__device__ __forceinline__ int T_as_int(double v) { return (int)__double_as_longlong(v); }
+
+constexpr int kLuLineExtra = 4;  // per broadcast line: 1/pivot, pivot-row rhs entry, pivot position, pad
 
 // Elimination on a register-resident system. On exit lane r holds (in LAPACK's final
 // layout) row `pos` of the packed LU factors, `bb` the forward-substituted right-hand side
@@ -104,6 +119,7 @@ __device__ __forceinline__ void lu_eliminate(T (&a)[NP], T& bb, int& pos, T& rdi
   constexpr int V = 16 / sizeof(T);
   constexpr int CPR = NP / V;
   const bool real = NP == 32 || lane < NP;
+  constexpr int LINE = NP + kLuLineExtra;
   pos = lane;
   rdiag = T(0);
   mypiv = lane;
@@ -113,14 +129,9 @@ __device__ __forceinline__ void lu_eliminate(T (&a)[NP], T& bb, int& pos, T& rdi
       // every lane inverts its own candidate while the pivot search is in flight; the pivot
       // lane's value is the 1/pivot everybody needs (same IEEE division, shorter critical path)
       const T rown = T(1) / a[k];
-      const int pl = pick_pivot(a[k], real && pos >= k, pos);
-      const T r = __shfl_sync(kFull, rown, pl);
-      const int ppos = __shfl_sync(kFull, pos, pl);
-      if (lane == k) mypiv = ppos;
-      if (pos == k) pos = ppos;
-      if (lane == pl) pos = k;
-      T* ub = urow + (k & 1) * NP;
-      if (lane == pl) {
+      const bool is_pl = pick_pivot(a[k], real && pos >= k, pos);
+      T* ub = urow + (k & 1) * LINE;
+      if (is_pl) {
 #pragma unroll
         for (int c = k / V; c < CPR; ++c) {
           VT v;
@@ -129,9 +140,16 @@ __device__ __forceinline__ void lu_eliminate(T (&a)[NP], T& bb, int& pos, T& rdi
           for (int e = 0; e < V; ++e) pv[e] = a[c * V + e];
           *reinterpret_cast<VT*>(ub + c * V) = v;
         }
+        T ex[kLuLineExtra] = {rown, bb, int_as_T(pos, T(0)), T(0)};
+#pragma unroll
+        for (int c = 0; c < kLuLineExtra / V; ++c) {
+          VT v;
+          T* pv = reinterpret_cast<T*>(&v);
+#pragma unroll
+          for (int e = 0; e < V; ++e) pv[e] = ex[c * V + e];
+          *reinterpret_cast<VT*>(ub + NP + c * V) = v;
+        }
       }
-      T bpk = T(0);
-      if (SOLVE) bpk = __shfl_sync(kFull, bb, pl);
       __syncwarp();
       T u[NP];
 #pragma unroll
@@ -141,7 +159,22 @@ __device__ __forceinline__ void lu_eliminate(T (&a)[NP], T& bb, int& pos, T& rdi
 #pragma unroll
         for (int e = 0; e < V; ++e) u[c * V + e] = pv[e];
       }
-      if (lane == pl) rdiag = r;
+      T ex[kLuLineExtra];
+#pragma unroll
+      for (int c = 0; c < kLuLineExtra / V; ++c) {
+        VT v = *reinterpret_cast<const VT*>(ub + NP + c * V);
+        const T* pv = reinterpret_cast<const T*>(&v);
+#pragma unroll
+        for (int e = 0; e < V; ++e) ex[c * V + e] = pv[e];
+      }
+      const T r = ex[0], bpk = ex[1];
+      const int ppos = T_as_int(ex[2]);  // physical position of the pivot row = piv[k]
+      if (lane == k) mypiv = ppos;
+      if (pos == k) pos = ppos;
+      if (is_pl) {
+        pos = k;
+        rdiag = r;
+      }
       if (real && pos > k) {
         const T l = a[k] * r;
         a[k] = l;
@@ -156,13 +189,14 @@ __device__ __forceinline__ void lu_eliminate(T (&a)[NP], T& bb, int& pos, T& rdi
 // Back substitution U x = y on the register-resident factors (rows addressed by `pos`).
 template <typename T, int NP, bool FULL>
 __device__ __forceinline__ T lu_backsolve(const T (&a)[NP], T bb, int pos, T rdiag, int lane,
-                                          int n) {
+                                          int n, T* slots /* 2 elements of shared memory */) {
   T mine = T(0);
 #pragma unroll
   for (int k = NP - 1; k >= 0; --k) {
     if (FULL || k < n) {
-      const int pl = __ffs(__ballot_sync(kFull, pos == k)) - 1;
-      const T xk = __shfl_sync(kFull, bb * rdiag, pl);
+      if (pos == k) slots[k & 1] = bb * rdiag;  // owner of final row k publishes x_k
+      __syncwarp();
+      const T xk = slots[k & 1];
       if (pos < k) bb = fma_(-a[k], xk, bb);
       if (lane == k) mine = xk;
     }
@@ -178,7 +212,7 @@ __global__ void __launch_bounds__(kLuWarps * 32, MINB)
                    int n, int fast) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  T* stage = reinterpret_cast<T*>(smem_raw) + (size_t)warp * (NP * NP + 2 * NP);
+  T* stage = reinterpret_cast<T*>(smem_raw) + (size_t)warp * (NP * NP + 2 * (NP + kLuLineExtra));
   T* urow = stage + NP * NP;
   const int64_t nwarps = (int64_t)gridDim.x * kLuWarps;
   int64_t sys = (int64_t)blockIdx.x * kLuWarps + warp;
@@ -224,7 +258,8 @@ __global__ void __launch_bounds__(kLuWarps * 32, MINB)
     }
     if (PIV != nullptr && lane < n) PIV[sys * n + lane] = mypiv;
     if (SOLVE) {
-      const T xm = lu_backsolve<T, NP, FULL>(a, bb, pos, rdiag, lane, n);
+      __syncwarp();
+      const T xm = lu_backsolve<T, NP, FULL>(a, bb, pos, rdiag, lane, n, urow);
       if (lane < n) X[sys * n + lane] = xm;
     }
   }
@@ -516,7 +551,7 @@ constexpr size_t kMaxSmem = 227 * 1024;
 template <typename T, int NP, bool SOLVE, bool FULL>
 int launch_lu_warp_impl(const T* A, int64_t sA, const T* b, int64_t sb, T* x, T* lu, int32_t* piv,
                         int64_t batch, int n, cudaStream_t st) {
-  const size_t smem = (size_t)kLuWarps * (NP * NP + 2 * NP) * sizeof(T);
+  const size_t smem = (size_t)kLuWarps * (NP * NP + 2 * (NP + kLuLineExtra)) * sizeof(T);
   auto kern = lu_warp_kernel<T, NP, SOLVE, FULL>;
   if constexpr (sizeof(T) == 4 && NP == 32 && SOLVE && FULL) {
     const char* e = getenv("LXB_LU_MINB");  // tuning knob: resident CTAs per SM the compiler targets
