@@ -16,6 +16,26 @@ namespace cgx = cooperative_groups;
 constexpr int kGridThreads = 256;
 constexpr int kGridMaxK = 72;  // widest reduction: QR panel (64), GMRES restart + 2 <= 72
 
+#ifdef LXB_QR_PROF
+// debug build only: per-phase nanosecond accumulators of CTA 0 (one copy per translation unit)
+static __device__ unsigned long long g_prof[16];
+__device__ __forceinline__ unsigned long long prof_now() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+#define LXB_PROF(slot)                                        \
+  do {                                                        \
+    if (blockIdx.x == 0 && threadIdx.x == 0) {                \
+      const unsigned long long t_ = prof_now();               \
+      g_prof[slot] += t_ - g_prof[15];                        \
+      g_prof[15] = t_;                                        \
+    }                                                         \
+  } while (0)
+#else
+#define LXB_PROF(slot)
+#endif
+
 template <typename T>
 struct GridTeam {
   cgx::grid_group g;
@@ -81,17 +101,36 @@ struct GridTeam {
     T* buf = part + (size_t)flip * kGridMaxK * nb;
     flip ^= 1;
     __syncthreads();
+    LXB_PROF(1);
     for (int k = tid; k < K; k += nt) buf[(size_t)k * nb + bid] = vals[k];
     __threadfence();
+    LXB_PROF(2);
     g.sync();
+    LXB_PROF(3);
     const int lane = tid & 31, warp = tid >> 5, nw = nt >> 5;
-    for (int k = warp; k < K; k += nw) {
-      T a = T(0);
-      for (int i = lane; i < nb; i += 32) a += __ldcg(buf + (size_t)k * nb + i);
-      a = warp_sum(a);
-      if (lane == 0) vals[k] = a;
+    // a warp sums 8 entries at a time so that their (independent) L2 loads overlap; the order
+    // of additions per entry is unchanged: lane-strided partial sums, then the shuffle tree
+    constexpr int KW = 8;
+    for (int k0 = warp; k0 < K; k0 += nw * KW) {
+      T a[KW];
+#pragma unroll
+      for (int q = 0; q < KW; ++q) a[q] = T(0);
+      for (int i = lane; i < nb; i += 32) {
+#pragma unroll
+        for (int q = 0; q < KW; ++q) {
+          const int k = k0 + q * nw;
+          if (k < K) a[q] += __ldcg(buf + (size_t)k * nb + i);
+        }
+      }
+#pragma unroll
+      for (int q = 0; q < KW; ++q) {
+        const int k = k0 + q * nw;
+        const T t = warp_sum(a[q]);
+        if (k < K && lane == 0) vals[k] = t;
+      }
     }
     __syncthreads();
+    LXB_PROF(4);
   }
 };
 

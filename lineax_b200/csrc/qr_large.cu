@@ -26,63 +26,141 @@ __device__ __forceinline__ T vmask(T stored, int grow, int j0, int c) {
 }
 
 // ------------------------------------------------------------------ K1: panel ----
+// Cooperative kernel, ONE 512-thread CTA per SM.  A CTA keeps its rows of the 32-column panel ON
+// CHIP for the whole factorisation: the first RR * 16 rows in registers (warp w holds rows w,
+// w+16, ...; lane = column, so a column broadcast is one shuffle) and the rest in shared memory
+// (in place in global memory, L2 resident, only when even that does not fit: XS = false).
+// Per column there is ONE sweep over the rows -- it applies reflector jj and accumulates the Gram
+// row of column jj+1 on the fly -- and ONE grid barrier: every CTA publishes its 32 partial Gram
+// sums (the pivot row's owner also the pivot row), and after the barrier every CTA sums the nb
+// partials itself, all loads in flight at once (measured on B200: the partial read is the
+// critical path of the column, 15 us when its L2 round trips serialise, < 2 us like this).
+constexpr int kPanelThreads = 512;
+constexpr int kPanelWarps = kPanelThreads / 32;
 template <typename T>
-__global__ void __launch_bounds__(kGridThreads)
+struct PanelCfg {
+  static constexpr int RR = sizeof(T) == 4 ? 40 : 20;  // register rows per warp
+  static constexpr int fixed_elems = 64 + 32 + 2 * kPB * kPB + kPanelWarps * 32 + 32;
+};
+
+template <typename T, bool XS>
+__global__ void __launch_bounds__(kPanelThreads, 1)
     qr_panel_kernel(T* __restrict__ a, T* __restrict__ taus, T* __restrict__ Tout, T* __restrict__ part,
-                    T* __restrict__ gpart, int m, int n, int j0, int nbw, int in_smem) {
+                    T* __restrict__ gpart, T* __restrict__ gfull, int m, int n, int j0, int nbw) {
+  constexpr int RR = PanelCfg<T>::RR;
+  constexpr int nw = kPanelWarps;
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  T* red = reinterpret_cast<T*>(smem_raw);   // 96 + kGridMaxK
-  T* vals = red + 96 + kGridMaxK;            // 64: [0,32) Gram row, [32,64) pivot row
+  T* vals = reinterpret_cast<T*>(smem_raw);  // 64: [0,32) Gram row, [32,64) pivot row
   T* fc = vals + 64;                         // 32
   T* Ts = fc + 32;                           // 32 x 32 T
   T* Gs = Ts + kPB * kPB;                    // 32 x 32 Gram of V
-  T* wsum = Gs + kPB * kPB;                  // 8 x 32 cross-warp scratch
-  T* Psm = wsum + 8 * 32;                    // rows_cta x 33 (shared-memory mode)
-  GridTeam<T> team(part, red);
-  const int tid = team.tid, nt = team.nt, lane = tid & 31, warp = tid >> 5, nw = nt >> 5;
-  int lo, hi;
-  team.slice(m - j0, lo, hi);  // local row indices within [j0, m)
+  T* wsum = Gs + kPB * kPB;                  // 16 x 32 cross-warp scratch
+  T* piv = wsum + nw * 32;                   // 32: pivot row of the next column
+  T* Psm = piv + 32;                         // extra rows x 33 (XS)
+  cgx::grid_group grid = cgx::this_grid();
+  const int nb = gridDim.x, bid = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int per = ((((m - j0) + nb - 1) / nb) + 3) & ~3;
+  const int lo = bid * per < m - j0 ? bid * per : m - j0;  // local row indices within [j0, m)
+  const int hi = lo + per < m - j0 ? lo + per : m - j0;
   const int nrows = hi - lo;
-  // The CTA's rows of the panel live in shared memory when they fit, otherwise they are worked on
-  // in place in global memory (the 32-column panel of a 262144-row matrix is 33.5 MB: L2-resident).
-  T* P = in_smem ? Psm : a + (size_t)(j0 + lo) * n + j0;
-  const size_t ldp = in_smem ? 33 : (size_t)n;
+  const int nreg = nrows < RR * nw ? nrows : RR * nw;  // local rows [0, nreg): registers
+  const int nx = nrows - nreg;                         // local rows [nreg, nrows): X
+  T* Xg = a + (size_t)(j0 + lo + nreg) * n + j0;
+  auto X = [&](int r, int c) -> T& { return XS ? Psm[r * 33 + c] : Xg[(size_t)r * n + c]; };
   const bool cok = lane < nbw;  // column guard (last, partial panel)
-  if (in_smem) {
-    for (int idx = tid; idx < nrows * kPB; idx += nt) {
+  // global scratch: 2 x (32 x nb partial sums + 32 pivot-row values), double buffered by column
+  const size_t pstride = (size_t)kPB * nb + kPB;
+#ifdef LXB_QR_PROF
+  if (blockIdx.x == 0 && threadIdx.x == 0) g_prof[15] = prof_now();
+#endif
+  T reg[RR];
+#pragma unroll
+  for (int q = 0; q < RR; ++q) {
+    const int r = q * nw + warp;
+    reg[q] = (r < nreg && cok) ? a[(size_t)(j0 + lo + r) * n + j0 + lane] : T(0);
+  }
+  if (XS) {
+    for (int idx = tid; idx < nx * kPB; idx += kPanelThreads) {
       const int r = idx / kPB, c = idx % kPB;
-      Psm[r * 33 + c] = c < nbw ? a[(size_t)(j0 + lo + r) * n + j0 + c] : T(0);
+      Psm[r * 33 + c] = c < nbw ? Xg[(size_t)r * n + c] : T(0);
     }
   }
   __syncthreads();
+  // Loop trip counts below are written in terms of block-uniform values only, so that the compiler
+  // can prove the shuffles convergent (otherwise every one of them is wrapped in a WARPSYNC).
+  const int xiters = (nx + 8 * nw - 1) / (8 * nw);
+  // Gram row of column 0 over the rows strictly below the diagonal (+ its pivot row); later
+  // columns get theirs from the update sweep of the previous column.
+  T carry = T(0);
+#pragma unroll
+  for (int q = 0; q < RR; ++q) {
+    const int r = q * nw + warp, lr = lo + r;
+    const T pj = __shfl_sync(kFull, reg[q], 0);
+    carry = (r < nreg && lr > 0) ? fma_(pj, reg[q], carry) : carry;
+    if (r < nreg && lr == 0) piv[lane] = reg[q];
+  }
+  for (int it = 0; it < xiters; ++it) {
+    const int r0 = warp + it * 8 * nw;
+    T pj[8], pc[8];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      const int r = r0 + q * nw;
+      const bool ok = r < nx && cok;
+      pj[q] = ok ? X(r, 0) : T(0);
+      pc[q] = ok ? X(r, lane) : T(0);
+    }
+#pragma unroll
+    for (int q = 0; q < 8; ++q) carry = fma_(pj[q], pc[q], carry);
+  }
   for (int jj = 0; jj < nbw; ++jj) {
     const int jrow = jj;  // local (panel) row index of the diagonal element: global row j0 + jj
-    // Gram row over own rows strictly below the diagonal + the pivot row itself
-    // 8 rows in flight per warp: the panel is L2-resident in global mode, so the loads must overlap
-    T acc = T(0);
-    for (int r0 = warp; r0 < nrows; r0 += 8 * nw) {
-      T pj[8], pc[8];
-#pragma unroll
-      for (int q = 0; q < 8; ++q) {
-        const int r = r0 + q * nw;
-        const bool ok = r < nrows && lo + r > jrow && cok;
-        pj[q] = ok ? P[r * ldp + jj] : T(0);
-        pc[q] = ok ? P[r * ldp + lane] : T(0);
-      }
-#pragma unroll
-      for (int q = 0; q < 8; ++q) acc = fma_(pj[q], pc[q], acc);
-    }
+    const T acc = carry;
     wsum[warp * 32 + lane] = acc;
     __syncthreads();
+    LXB_PROF(0);
+    T* buf = part + (size_t)(jj & 1) * pstride;
     if (warp == 0) {
       T s = T(0);
+#pragma unroll
       for (int w = 0; w < nw; ++w) s += wsum[w * 32 + lane];
-      vals[lane] = s;
-      const bool owner = jrow >= lo && jrow < hi;
-      vals[32 + lane] = (owner && cok) ? P[(jrow - lo) * ldp + lane] : T(0);
+      buf[(size_t)lane * nb + bid] = s;
+      if (jrow >= lo && jrow < hi) buf[(size_t)kPB * nb + lane] = cok ? piv[lane] : T(0);
+      __threadfence();
+    }
+    LXB_PROF(1);
+    grid.sync();
+    LXB_PROF(2);
+    {
+      // warp w sums entries 2w and 2w+1 over the nb partials, lanes striding the CTAs
+      const T* b0 = buf + (size_t)(2 * warp) * nb;
+      const T* b1 = b0 + nb;
+      T s0 = T(0), s1 = T(0);
+      for (int i0 = lane; i0 < nb; i0 += 32 * 5) {
+        T t0[5], t1[5];
+#pragma unroll
+        for (int u = 0; u < 5; ++u) {
+          const int i = i0 + 32 * u;
+          t0[u] = i < nb ? __ldcg(b0 + i) : T(0);
+          t1[u] = i < nb ? __ldcg(b1 + i) : T(0);
+        }
+#pragma unroll
+        for (int u = 0; u < 5; ++u) {
+          s0 += t0[u];
+          s1 += t1[u];
+        }
+      }
+      T pv = T(0);
+      if (warp == 0) pv = __ldcg(buf + (size_t)kPB * nb + lane);
+      s0 = warp_sum(s0);
+      s1 = warp_sum(s1);
+      if (lane == 0) {
+        vals[2 * warp] = s0;
+        vals[2 * warp + 1] = s1;
+      }
+      if (warp == 0) vals[32 + lane] = pv;
     }
     __syncthreads();
-    team.reduce_dyn(vals, 64);
+    LXB_PROF(3);
     // larfg
     const T alpha = vals[32 + jj], ssq = vals[jj];
     T tau = T(0), beta = alpha, scal = T(1);
@@ -92,62 +170,88 @@ __global__ void __launch_bounds__(kGridThreads)
       tau = (beta - alpha) / beta;
       scal = T(1) / (alpha - beta);
     }
-    if (tid < 32) fc[tid] = tid > jj && tid < nbw ? tau * (vals[32 + tid] + scal * vals[tid]) : T(0);
-    __syncthreads();
-    // v = scal * a[:, jj] below the diagonal; trailing panel columns -= f_c v
-    const T fcl = fc[lane];
-    for (int r0 = warp; r0 < nrows; r0 += 8 * nw) {
-      T pj[8], pc[8];
+    // f_c = tau * (pivot-row entry + v^T a_c) for the panel columns right of jj
+    const T fcl = (lane > jj && cok) ? tau * (vals[32 + lane] + scal * vals[lane]) : T(0);
+    LXB_PROF(4);
+    // v = scal * a[:, jj] below the diagonal; trailing panel columns -= f_c v; and, in the same
+    // sweep, the Gram row of column jj + 1 from the updated values.  Branch-free on purpose.
+    const int jn = jj + 1;
+    const bool more = jn < nbw;
+    const bool right = lane > jj;
+    carry = T(0);
+#pragma unroll
+    for (int q = 0; q < RR; ++q) {
+      const int r = q * nw + warp, lr = lo + r;
+      const bool live = r < nreg && cok;
+      const T old = reg[q];
+      const T v = __shfl_sync(kFull, old, jj) * scal;
+      const T below = right ? fma_(-fcl, v, old) : v;  // rows under the diagonal
+      const T ondiag = right ? old - fcl : beta;       // the pivot row
+      const T cand = lr > jrow ? below : ondiag;
+      const T nv = (live && lr >= jrow && lane >= jj) ? cand : old;
+      reg[q] = nv;
+      const T pn = __shfl_sync(kFull, nv, jn & 31);
+      carry = (more && live && lr > jrow + 1) ? fma_(pn, nv, carry) : carry;
+      if (more && r < nreg && lr == jrow + 1) piv[lane] = cok ? nv : T(0);
+    }
+    // extra rows (always strictly below the panel's diagonal block: nreg >= 32 whenever nx > 0)
+    for (int it = 0; it < xiters; ++it) {
+      const int r0 = warp + it * 8 * nw;
+      T pc[8];
 #pragma unroll
       for (int q = 0; q < 8; ++q) {
         const int r = r0 + q * nw;
-        const bool ok = r < nrows && lo + r >= jrow && cok;
-        pj[q] = ok ? P[r * ldp + jj] : T(0);
-        pc[q] = ok ? P[r * ldp + lane] : T(0);
+        pc[q] = (r < nx && cok) ? X(r, lane) : T(0);
       }
-      __syncwarp();
 #pragma unroll
       for (int q = 0; q < 8; ++q) {
         const int r = r0 + q * nw;
-        if (r >= nrows || !cok) continue;
-        const int lr = lo + r;
-        if (lr > jrow) {
-          const T v = pj[q] * scal;
-          if (lane == jj) P[r * ldp + jj] = v;
-          else if (lane > jj) P[r * ldp + lane] = fma_(-fcl, v, pc[q]);
-        } else if (lr == jrow) {
-          if (lane == jj) P[r * ldp + jj] = beta;
-          else if (lane > jj) P[r * ldp + lane] = pc[q] - fcl;
-        }
+        const bool live = r < nx && cok;
+        const T v = __shfl_sync(kFull, pc[q], jj) * scal;
+        const T nv = lane >= jj ? (right ? fma_(-fcl, v, pc[q]) : v) : pc[q];
+        if (live && lane >= jj) X(r, lane) = nv;
+        const T pn = __shfl_sync(kFull, nv, jn & 31);
+        carry = (more && live) ? fma_(pn, nv, carry) : carry;
       }
     }
-    if (team.bid == 0 && tid == 0) taus[j0 + jj] = tau;
+    if (bid == 0 && tid == 0) taus[j0 + jj] = tau;
     if (tid == 0) Ts[jj * kPB + jj] = tau;  // diagonal of T
-    __syncthreads();
+    LXB_PROF(5);
   }
+  __syncthreads();
   // write the factored panel back
-  if (in_smem) {
-    for (int idx = tid; idx < nrows * kPB; idx += nt) {
+#pragma unroll
+  for (int q = 0; q < RR; ++q) {
+    const int r = q * nw + warp;
+    if (r < nreg && cok) a[(size_t)(j0 + lo + r) * n + j0 + lane] = reg[q];
+  }
+  if (XS) {
+    for (int idx = tid; idx < nx * kPB; idx += kPanelThreads) {
       const int r = idx / kPB, c = idx % kPB;
-      if (c < nbw) a[(size_t)(j0 + lo + r) * n + j0 + c] = Psm[r * 33 + c];
+      if (c < nbw) Xg[(size_t)r * n + c] = Psm[r * 33 + c];
     }
   }
-  // Gram of V (unit lower trapezoidal): G[c1][c2] = sum_i v(i,c1) v(i,c2), per-CTA partial -> global
-  // warps split the rows (each row is read once as a coalesced 128-byte line and kept in a register
-  // per lane); lane = column c2; the 32 columns c1 are broadcast with shuffles
+  // Gram of V (unit lower trapezoidal): G[c1][c2] = sum_i v(i,c1) v(i,c2), per-CTA partial -> global.
+  // lane = column c2; the 32 columns c1 are broadcast with shuffles
   {
     T g[kPB];
 #pragma unroll
     for (int c1 = 0; c1 < kPB; ++c1) g[c1] = T(0);
-    for (int r = warp; r < nrows; r += nw) {
-      const int gr = j0 + lo + r;
-      const T mine = cok ? vmask<T>(P[r * ldp + lane], gr, j0, lane) : T(0);
+#pragma unroll
+    for (int q = 0; q < RR; ++q) {
+      const int r = q * nw + warp;
+      const T mine = (r < nreg && cok) ? vmask<T>(reg[q], j0 + lo + r, j0, lane) : T(0);
 #pragma unroll
       for (int c1 = 0; c1 < kPB; ++c1) g[c1] = fma_(__shfl_sync(kFull, mine, c1), mine, g[c1]);
     }
-    // cross-warp sum through shared memory (Gs reused as scratch: 8 warps x 32 x 32 does not fit,
-    // so accumulate warp by warp)
-    for (int e = tid; e < kPB * kPB; e += nt) Gs[e] = T(0);
+    for (int it = 0; it < (nx + nw - 1) / nw; ++it) {
+      const int r = warp + it * nw;
+      const T mine = (r < nx && cok) ? X(r, lane) : T(0);
+#pragma unroll
+      for (int c1 = 0; c1 < kPB; ++c1) g[c1] = fma_(__shfl_sync(kFull, mine, c1), mine, g[c1]);
+    }
+    // cross-warp sum through shared memory, warp by warp (fixed order)
+    for (int e = tid; e < kPB * kPB; e += kPanelThreads) Gs[e] = T(0);
     __syncthreads();
     for (int w = 0; w < nw; ++w) {
       if (warp == w) {
@@ -156,15 +260,31 @@ __global__ void __launch_bounds__(kGridThreads)
       }
       __syncthreads();
     }
-    for (int e = tid; e < kPB * kPB; e += nt) gpart[(size_t)team.bid * (kPB * kPB) + e] = Gs[e];
+    for (int e = tid; e < kPB * kPB; e += kPanelThreads) gpart[(size_t)bid * (kPB * kPB) + e] = Gs[e];
+  }
+  LXB_PROF(6);
+  __threadfence();
+  grid.sync();
+  LXB_PROF(7);
+  // two-level sum of the per-CTA Gram partials: CTA b < 32 reduces row b, CTA 0 then builds T
+  if (bid < kPB) {
+    const int e0 = bid * kPB + warp * 2;  // 2 entries per warp
+    T s[2] = {T(0), T(0)};
+    for (int b = lane; b < nb; b += 32) {
+#pragma unroll
+      for (int u = 0; u < 2; ++u) s[u] += __ldcg(gpart + (size_t)b * (kPB * kPB) + e0 + u);
+    }
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      const T t = warp_sum(s[u]);
+      if (lane == 0) gfull[e0 + u] = t;
+    }
   }
   __threadfence();
-  team.sync();
-  for (int e = tid; e < kPB * kPB; e += nt) {
-    T s = T(0);
-    for (int b = 0; b < team.nb; ++b) s += __ldcg(gpart + (size_t)b * (kPB * kPB) + e);
-    Gs[e] = s;
-  }
+  grid.sync();
+  LXB_PROF(8);
+  if (bid != 0) return;
+  for (int e = tid; e < kPB * kPB; e += kPanelThreads) Gs[e] = __ldcg(gfull + e);
   __syncthreads();
   // larft (forward, columnwise): T[0:j, j] = -tau_j * T[0:j, 0:j] * G[0:j, j]
   for (int j = 1; j < nbw; ++j) {
@@ -178,180 +298,401 @@ __global__ void __launch_bounds__(kGridThreads)
     if (tid < j) Ts[tid * kPB + j] = fc[tid];
     __syncthreads();
   }
-  if (team.bid == 0) {
-    for (int e = tid; e < kPB * kPB; e += nt) {
-      const int r = e / kPB, c = e % kPB;
-      Tout[e] = (c >= r && c < nbw && r < nbw) ? Ts[e] : T(0);
-    }
+  for (int e = tid; e < kPB * kPB; e += kPanelThreads) {
+    const int r = e / kPB, c = e % kPB;
+    Tout[e] = (c >= r && c < nbw && r < nbw) ? Ts[e] : T(0);
   }
+  LXB_PROF(9);
 }
 
 // ------------------------------------------------------------- K2: W partial ----
-// Wp[g][k][c] = sum_{i in row group g} v(i,k) * A[i][cbase + c]; CTA tile = 32 k x 256 columns,
-// thread tile 4 k x 8 columns (32 FMA per 3 LDS.128); the next 32-row chunk is prefetched from
-// global memory into registers while the current one is consumed from shared memory.
+// Wp[g][k][c] = sum_{i in row group g} v(i,k) * A[i][cbase + c].  CTA tile = 32 k x 256 columns,
+// 4 warps; warp w owns k = 8w..8w+7, lane l owns columns 4l..4l+3 and 128+4l..128+4l+3, so one
+// row step is 64 FMA per 4 LDS.128 (two of them warp-wide broadcasts, two conflict-free).
+// 16-row chunks of V and A2 travel global -> shared with cp.async (zero-filled past the group /
+// tile edge) through a 3-stage ring, so no staging registers and no STS in the loop.
 constexpr int kW2Tile = 256;
+constexpr int kW2Rows = 16;
+constexpr int kW2Stages = 3;
+constexpr int kW2Threads = 128;
+constexpr int kW2MaxGroups = 128;
+
+__device__ __forceinline__ void cp_async_zfill(void* smem_dst, const void* gmem_src, int bytes,
+                                               int src_bytes) {
+  const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+  if (bytes == 16)
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(d), "l"(gmem_src), "r"(src_bytes));
+  else if (bytes == 8)
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;\n" ::"r"(d), "l"(gmem_src), "r"(src_bytes));
+  else
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;\n" ::"r"(d), "l"(gmem_src), "r"(src_bytes));
+}
+
+// 4 consecutive elements from 16-byte aligned shared memory
 template <typename T>
-__global__ void __launch_bounds__(256)
+__device__ __forceinline__ void lds4(const T* p, T* out) {
+  using VT = typename V16K<T>::type;
+  constexpr int V = 16 / sizeof(T);
+#pragma unroll
+  for (int h = 0; h < 4 / V; ++h) {
+    const VT t = reinterpret_cast<const VT*>(p)[h];
+    const T* pt = reinterpret_cast<const T*>(&t);
+#pragma unroll
+    for (int e = 0; e < V; ++e) out[h * V + e] = pt[e];
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kW2Threads, sizeof(T) == 4 ? 4 : 2)
     qr_wpartial_kernel(const T* __restrict__ a, T* __restrict__ Wp, int m, int n, int j0, int ncols,
                        int ngroups) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  T(*Vs)[kPB] = reinterpret_cast<T(*)[kPB]>(smem_raw);                              // [32][32]
-  T(*As)[kW2Tile] = reinterpret_cast<T(*)[kW2Tile]>(smem_raw + 32 * kPB * sizeof(T));  // [32][256]
-  const int tid = threadIdx.x;
+  constexpr int kStageElems = kW2Rows * (kPB + kW2Tile);
+  T* stage0 = reinterpret_cast<T*>(smem_raw);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int tile = blockIdx.x, grp = blockIdx.y;
   const int cbase = j0 + kPB + tile * kW2Tile;
   const int cw = min(kW2Tile, j0 + kPB + ncols - cbase);
   const int rows_total = m - j0;
-  const int per = (((rows_total + ngroups - 1) / ngroups) + 31) & ~31;
+  const int per = (((rows_total + ngroups - 1) / ngroups) + kW2Rows - 1) / kW2Rows * kW2Rows;
   const int r0 = j0 + grp * per, r1 = min(m, r0 + per);
-  const int kq = tid >> 5, cq = tid & 31;  // 8 groups of 4 k's, 32 groups of 8 columns
-  T acc[4][8];
+  constexpr int V = 16 / sizeof(T);
+  // 16-byte pieces need aligned row starts (j0 and cbase are multiples of 32 elements)
+  const bool al = (n % V == 0) && ((reinterpret_cast<uintptr_t>(a) & 15) == 0);
+  T acc[8][8];
 #pragma unroll
-  for (int x = 0; x < 4; ++x)
+  for (int x = 0; x < 8; ++x)
 #pragma unroll
     for (int y = 0; y < 8; ++y) acc[x][y] = T(0);
-  // staging assignment: V chunk 32x32 -> 4 elements per thread; A chunk 32x256 -> 32 per thread
-  T pv[4], pa[32];
-  auto fetch = [&](int rb) {
+
+  auto issue = [&](int st, int rb) {
+    T* Vs = stage0 + (size_t)st * kStageElems;  // [16][32]
+    T* As = Vs + kW2Rows * kPB;                 // [16][256]
+    if (al) {
+      constexpr int vp = kPB / V, ap = kW2Tile / V;  // pieces per row
 #pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      const int idx = tid + q * 256, r = idx / kPB, c = idx % kPB, gr = rb + r;
-      pv[q] = gr < r1 ? vmask<T>(a[(size_t)gr * n + j0 + c], gr, j0, c) : T(0);
-    }
+      for (int q = 0; q < kW2Rows * vp / kW2Threads; ++q) {
+        const int pc = tid + q * kW2Threads, r = pc / vp, c = (pc % vp) * V, gr = rb + r;
+        const bool ok = gr < r1;
+        cp_async_zfill(Vs + r * kPB + c, ok ? a + (size_t)gr * n + j0 + c : a, 16, ok ? 16 : 0);
+      }
 #pragma unroll
-    for (int q = 0; q < 32; ++q) {
-      const int idx = tid + q * 256, r = idx / kW2Tile, c = idx % kW2Tile, gr = rb + r;
-      pa[q] = (gr < r1 && c < cw) ? a[(size_t)gr * n + cbase + c] : T(0);
+      for (int q = 0; q < kW2Rows * ap / kW2Threads; ++q) {
+        const int pc = tid + q * kW2Threads, r = pc / ap, c = (pc % ap) * V, gr = rb + r;
+        int nb = gr < r1 ? (cw - c) * (int)sizeof(T) : 0;
+        nb = nb < 0 ? 0 : (nb > 16 ? 16 : nb);
+        cp_async_zfill(As + r * kW2Tile + c, nb ? a + (size_t)gr * n + cbase + c : a, 16, nb);
+      }
+    } else {
+      for (int e = tid; e < kW2Rows * kPB; e += kW2Threads) {
+        const int r = e / kPB, c = e % kPB, gr = rb + r;
+        const bool ok = gr < r1;
+        cp_async_zfill(Vs + e, ok ? a + (size_t)gr * n + j0 + c : a, (int)sizeof(T), ok ? (int)sizeof(T) : 0);
+      }
+      for (int e = tid; e < kW2Rows * kW2Tile; e += kW2Threads) {
+        const int r = e / kW2Tile, c = e % kW2Tile, gr = rb + r;
+        const bool ok = gr < r1 && c < cw;
+        cp_async_zfill(As + e, ok ? a + (size_t)gr * n + cbase + c : a, (int)sizeof(T),
+                       ok ? (int)sizeof(T) : 0);
+      }
     }
   };
-  if (r0 < r1) fetch(r0);
-  for (int rb = r0; rb < r1; rb += 32) {
+
+  const int nchunks = r1 > r0 ? (r1 - r0 + kW2Rows - 1) / kW2Rows : 0;
 #pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      const int idx = tid + q * 256;
-      Vs[idx / kPB][idx % kPB] = pv[q];
-    }
-#pragma unroll
-    for (int q = 0; q < 32; ++q) {
-      const int idx = tid + q * 256;
-      As[idx / kW2Tile][idx % kW2Tile] = pa[q];
-    }
+  for (int sidx = 0; sidx < kW2Stages - 1; ++sidx) {
+    if (sidx < nchunks) issue(sidx, r0 + sidx * kW2Rows);
+    cp_async_commit();
+  }
+  for (int ch = 0; ch < nchunks; ++ch) {
+    cp_async_wait<kW2Stages - 2>();
     __syncthreads();
-    if (rb + 32 < r1) fetch(rb + 32);
-#pragma unroll 4
-    for (int r = 0; r < 32; ++r) {
-      T v[4], x[8];
+    const int nx = ch + kW2Stages - 1;
+    if (nx < nchunks) issue(nx % kW2Stages, r0 + nx * kW2Rows);
+    cp_async_commit();
+    T* Vs = stage0 + (size_t)(ch % kW2Stages) * kStageElems;
+    const T* As = Vs + kW2Rows * kPB;
+    const int rb = r0 + ch * kW2Rows;
+    if (rb < j0 + kPB) {  // rows crossing the panel's diagonal block: unit diagonal, zeros above
+      for (int e = tid; e < kW2Rows * kPB; e += kW2Threads) {
+        const int r = e / kPB, c = e % kPB, gr = rb + r;
+        Vs[e] = gr < r1 ? vmask<T>(Vs[e], gr, j0, c) : T(0);
+      }
+      __syncthreads();
+    }
+#pragma unroll 2
+    for (int r = 0; r < kW2Rows; ++r) {
+      T v[8], x[8];
+      lds4<T>(Vs + r * kPB + 8 * warp, v);
+      lds4<T>(Vs + r * kPB + 8 * warp + 4, v + 4);
+      lds4<T>(As + r * kW2Tile + 4 * lane, x);
+      lds4<T>(As + r * kW2Tile + 128 + 4 * lane, x + 4);
 #pragma unroll
-      for (int e = 0; e < 4; ++e) v[e] = Vs[r][4 * kq + e];
-#pragma unroll
-      for (int e = 0; e < 8; ++e) x[e] = As[r][8 * cq + e];
-#pragma unroll
-      for (int p = 0; p < 4; ++p)
+      for (int p = 0; p < 8; ++p)
 #pragma unroll
         for (int q = 0; q < 8; ++q) acc[p][q] = fma_(v[p], x[q], acc[p][q]);
     }
-    __syncthreads();
   }
+  cp_async_wait<0>();
   T* out = Wp + ((size_t)grp * kPB) * ncols;
 #pragma unroll
-  for (int p = 0; p < 4; ++p)
+  for (int p = 0; p < 8; ++p)
 #pragma unroll
     for (int q = 0; q < 8; ++q) {
-      const int c = tile * kW2Tile + 8 * cq + q;
-      if (c < ncols) out[(size_t)(4 * kq + p) * ncols + c] = acc[p][q];
+      const int c = tile * kW2Tile + (q < 4 ? 4 * lane + q : 128 + 4 * lane + q - 4);
+      if (c < ncols) out[(size_t)(8 * warp + p) * ncols + c] = acc[p][q];
     }
 }
 
 // -------------------------------------------------------------- K3: W finish ----
-// W2[k][c] = sum_k' T[k'][k] * (sum_g Wp[g][k'][c])
+// W2[k][c] = sum_k' T[k'][k] * (sum_g Wp[g][k'][c]); 32 columns x 8 slices of 4 k per CTA.  The
+// group sum is latency bound (a few loads per thread), so 8 groups x 4 k are loaded before any add.
+constexpr int kWfCols = 32;
 template <typename T>
 __global__ void __launch_bounds__(256)
     qr_wfinish_kernel(const T* __restrict__ Wp, const T* __restrict__ Tm, T* __restrict__ W2, int ncols,
                       int ngroups) {
   __shared__ T Ts[kPB * kPB];
+  __shared__ T wsum[kPB][kWfCols + 1];
   for (int e = threadIdx.x; e < kPB * kPB; e += blockDim.x) Ts[e] = Tm[e];
-  __syncthreads();
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= ncols) return;
-  T w[kPB];
+  const int cl = threadIdx.x & (kWfCols - 1), ks = threadIdx.x / kWfCols;  // ks: 0..7
+  const int c = blockIdx.x * kWfCols + cl;
+  if (c < ncols) {
+    T w[4] = {T(0), T(0), T(0), T(0)};
+    for (int g0 = 0; g0 < ngroups; g0 += 8) {
+      T t[8][4];
 #pragma unroll
-  for (int k = 0; k < kPB; ++k) {
-    T s = T(0);
-    for (int g = 0; g < ngroups; ++g) s += Wp[((size_t)g * kPB + k) * ncols + c];
-    w[k] = s;
+      for (int u = 0; u < 8; ++u)
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          t[u][k] = g0 + u < ngroups ? Wp[((size_t)(g0 + u) * kPB + 4 * ks + k) * ncols + c] : T(0);
+#pragma unroll
+      for (int u = 0; u < 8; ++u)
+#pragma unroll
+        for (int k = 0; k < 4; ++k) w[k] += t[u][k];
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) wsum[4 * ks + k][cl] = w[k];
   }
+  __syncthreads();
+  if (c >= ncols) return;
 #pragma unroll
-  for (int k = 0; k < kPB; ++k) {
+  for (int kk = 0; kk < 4; ++kk) {
+    const int k = 4 * ks + kk;
     T s = T(0);
-#pragma unroll
-    for (int kp = 0; kp <= k; ++kp) s = fma_(Ts[kp * kPB + k], w[kp], s);  // T upper triangular
+    for (int kp = 0; kp <= k; ++kp) s = fma_(Ts[kp * kPB + k], wsum[kp][cl], s);  // T upper triangular
     W2[(size_t)k * ncols + c] = s;
   }
 }
 
 // ------------------------------------------------------------------ K4: update ----
-// A[i][cbase + c] -= sum_k v(i,k) W2[k][c]; CTA tile 64 rows x 128 columns, thread 4 x 8.
+// A[i][cbase + c] -= sum_k v(i,k) W2[k][c].
+// Fallback for rows that are not 16-byte aligned: one 128 x 128 tile per CTA, thread tile 8 x 8.
+constexpr int kUpRows = 128, kUpCols = 128, kUpLd = kUpRows + 4;
 template <typename T>
-__global__ void __launch_bounds__(256)
-    qr_update_kernel(T* __restrict__ a, const T* __restrict__ W2, int m, int n, int j0, int ncols) {
-  __shared__ __align__(16) T Vt[kPB][64];
-  __shared__ __align__(16) T Ws[kPB][128];
+__global__ void __launch_bounds__(256, sizeof(T) == 4 ? 2 : 1)
+    qr_update_simple_kernel(T* __restrict__ a, const T* __restrict__ W2, int m, int n, int j0, int ncols) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  T* Vt = reinterpret_cast<T*>(smem_raw);  // [32][132]: V tile transposed, padded against conflicts
+  T* Ws = Vt + kPB * kUpLd;                // [32][128]
   const int tid = threadIdx.x;
   const int tile = blockIdx.x, rblk = blockIdx.y;
-  const int cbase = j0 + kPB + tile * 128;
-  const int rb = j0 + rblk * 64;
-  for (int idx = tid; idx < 64 * kPB; idx += 256) {
+  const int cbase = j0 + kPB + tile * kUpCols;
+  const int rb = j0 + rblk * kUpRows;
+  for (int idx = tid; idx < kUpRows * kPB; idx += 256) {
     const int r = idx / kPB, c = idx % kPB, gr = rb + r;
-    Vt[c][r] = gr < m ? vmask<T>(a[(size_t)gr * n + j0 + c], gr, j0, c) : T(0);
+    Vt[c * kUpLd + r] = gr < m ? vmask<T>(a[(size_t)gr * n + j0 + c], gr, j0, c) : T(0);
   }
-  for (int idx = tid; idx < kPB * 128; idx += 256) {
-    const int k = idx / 128, c = idx % 128;
-    const int gc = tile * 128 + c;
-    Ws[k][c] = gc < ncols ? W2[(size_t)k * ncols + gc] : T(0);
+  for (int idx = tid; idx < kPB * kUpCols; idx += 256) {
+    const int k = idx / kUpCols, c = idx % kUpCols;
+    const int gc = tile * kUpCols + c;
+    Ws[k * kUpCols + c] = gc < ncols ? W2[(size_t)k * ncols + gc] : T(0);
   }
   __syncthreads();
-  const int ri = tid >> 4, ci = tid & 15;  // 16 row groups of 4, 16 column groups of 8
-  T acc[4][8];
+  const int ri = tid >> 4, ci = tid & 15;  // 16 row groups of 8, 16 column groups of 4 + 4
+  T acc[8][8];
 #pragma unroll
-  for (int p = 0; p < 4; ++p)
+  for (int p = 0; p < 8; ++p)
 #pragma unroll
     for (int q = 0; q < 8; ++q) acc[p][q] = T(0);
-#pragma unroll 8
+#pragma unroll 4
   for (int k = 0; k < kPB; ++k) {
-    T v[4], w[8];
+    T v[8], w[8];
+    lds4<T>(Vt + k * kUpLd + 8 * ri, v);
+    lds4<T>(Vt + k * kUpLd + 8 * ri + 4, v + 4);
+    lds4<T>(Ws + k * kUpCols + 4 * ci, w);
+    lds4<T>(Ws + k * kUpCols + 64 + 4 * ci, w + 4);
 #pragma unroll
-    for (int p = 0; p < 4; ++p) v[p] = Vt[k][4 * ri + p];
-#pragma unroll
-    for (int q = 0; q < 8; ++q) w[q] = Ws[k][8 * ci + q];
-#pragma unroll
-    for (int p = 0; p < 4; ++p)
+    for (int p = 0; p < 8; ++p)
 #pragma unroll
       for (int q = 0; q < 8; ++q) acc[p][q] = fma_(v[p], w[q], acc[p][q]);
   }
   using VT = typename V16K<T>::type;
   constexpr int V = 16 / sizeof(T);
   const bool vec = (n % V == 0) && ((reinterpret_cast<uintptr_t>(a) & 15) == 0) &&
-                   (tile * 128 + 8 * ci + 8 <= ncols);
+                   (tile * kUpCols + kUpCols <= ncols);
+  if (vec) {
+    // 4 rows at a time: all loads of the group are issued before the first dependent store
 #pragma unroll
-  for (int p = 0; p < 4; ++p) {
-    const int gr = rb + 4 * ri + p;
-    if (gr >= m) continue;
-    T* rowp = a + (size_t)gr * n + cbase + 8 * ci;
-    if (vec) {
+    for (int pg = 0; pg < 2; ++pg) {
+      VT val[4][2][4 / V];
 #pragma unroll
-      for (int h = 0; h < 8 / V; ++h) {
-        VT val = reinterpret_cast<VT*>(rowp)[h];
-        T* pv = reinterpret_cast<T*>(&val);
+      for (int p = 0; p < 4; ++p) {
+        const int gr = rb + 8 * ri + 4 * pg + p;
 #pragma unroll
-        for (int e = 0; e < V; ++e) pv[e] = pv[e] - acc[p][h * V + e];
-        reinterpret_cast<VT*>(rowp)[h] = val;
+        for (int h = 0; h < 2; ++h)
+#pragma unroll
+          for (int u = 0; u < 4 / V; ++u)
+            if (gr < m)
+              val[p][h][u] = reinterpret_cast<const VT*>(a + (size_t)gr * n + cbase + 64 * h + 4 * ci)[u];
       }
-    } else {
+#pragma unroll
+      for (int p = 0; p < 4; ++p) {
+        const int gr = rb + 8 * ri + 4 * pg + p;
+        if (gr >= m) continue;
+#pragma unroll
+        for (int h = 0; h < 2; ++h)
+#pragma unroll
+          for (int u = 0; u < 4 / V; ++u) {
+            T* pv = reinterpret_cast<T*>(&val[p][h][u]);
+#pragma unroll
+            for (int e = 0; e < V; ++e) pv[e] = pv[e] - acc[4 * pg + p][4 * h + u * V + e];
+            reinterpret_cast<VT*>(a + (size_t)gr * n + cbase + 64 * h + 4 * ci)[u] = val[p][h][u];
+          }
+      }
+    }
+  } else {
+#pragma unroll
+    for (int p = 0; p < 8; ++p) {
+      const int gr = rb + 8 * ri + p;
+      if (gr >= m) continue;
 #pragma unroll
       for (int q = 0; q < 8; ++q) {
-        const int gc = tile * 128 + 8 * ci + q;
-        if (gc < ncols) rowp[q] = rowp[q] - acc[p][q];
+        const int cc = (q < 4 ? 4 * ci + q : 64 + 4 * ci + q - 4);
+        const int gc = tile * kUpCols + cc;
+        if (gc < ncols) {
+          T* pp = a + (size_t)gr * n + cbase + cc;
+          *pp = *pp - acc[p][q];
+        }
+      }
+    }
+  }
+}
+
+// Main path (16-byte aligned rows).  A CTA owns one 128-column tile and walks a strip of row
+// blocks (RT = 128 rows fp32 / 64 rows fp64).  W2's tile stays in shared memory for the whole
+// strip; per row block the A2 tile is fetched global -> shared by cp.async while the block's
+// FMAs run (it is only needed by the epilogue), and the V tile of the NEXT block is fetched,
+// transposed and XOR-swizzled, into the other half of a double buffer.  No global load is ever
+// waited on in the FMA loop.  Thread tile MR x 8 (MR = 8 fp32 / 4 fp64).
+template <typename T>
+struct UpCfg {
+  static constexpr int MR = sizeof(T) == 4 ? 8 : 4;
+  static constexpr int RT = 16 * MR;
+  static constexpr size_t smem = ((size_t)kPB * kUpCols + 2 * (size_t)kPB * RT + (size_t)RT * kUpCols) * sizeof(T);
+};
+__device__ __forceinline__ int up_swz(int k) { return (k & 7) << 2; }
+
+template <typename T>
+__global__ void __launch_bounds__(256, sizeof(T) == 4 ? 2 : 1)
+    qr_update_kernel(T* __restrict__ a, const T* __restrict__ W2, int m, int n, int j0, int ncols,
+                     int rblocks, int per_strip) {
+  constexpr int MR = UpCfg<T>::MR, RT = UpCfg<T>::RT;
+  constexpr int V = 16 / sizeof(T);
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  T* Ws = reinterpret_cast<T*>(smem_raw);  // [32][128]
+  T* Vt = Ws + kPB * kUpCols;              // 2 x [32][RT], element (k, r) at k*RT + (r ^ swz(k))
+  T* At = Vt + 2 * kPB * RT;               // [RT][128]
+  const int tid = threadIdx.x;
+  const int tile = blockIdx.x;
+  const int cbase = j0 + kPB + tile * kUpCols;
+  const int cw = min(kUpCols, ncols - tile * kUpCols);
+  const int b0 = blockIdx.y * per_strip, b1 = min(rblocks, b0 + per_strip);
+  if (b0 >= b1) return;
+  for (int idx = tid; idx < kPB * kUpCols; idx += 256) {
+    const int k = idx / kUpCols, c = idx % kUpCols;
+    Ws[idx] = c < cw ? W2[(size_t)k * ncols + tile * kUpCols + c] : T(0);
+  }
+  auto issue_v = [&](int buf, int b) {
+    T* dst = Vt + buf * (kPB * RT);
+    const int rb = j0 + b * RT;
+#pragma unroll
+    for (int q = 0; q < kPB * RT / 256; ++q) {
+      const int e = tid + q * 256;
+      const int k = ((e >> 5) & 3) * 8 + (e & 7), r = (e >> 7) * 4 + ((e >> 3) & 3), gr = rb + r;
+      const bool ok = gr < m;
+      cp_async_zfill(dst + k * RT + (r ^ up_swz(k)), ok ? a + (size_t)gr * n + j0 + k : a, (int)sizeof(T),
+                     ok ? (int)sizeof(T) : 0);
+    }
+  };
+  auto issue_a = [&](int b) {
+    const int rb = j0 + b * RT;
+    constexpr int ppr = kUpCols / V;  // 16-byte pieces per row
+#pragma unroll
+    for (int q = 0; q < RT * ppr / 256; ++q) {
+      const int pc = tid + q * 256, r = pc / ppr, c = (pc % ppr) * V, gr = rb + r;
+      int nb = gr < m ? (cw - c) * (int)sizeof(T) : 0;
+      nb = nb < 0 ? 0 : (nb > 16 ? 16 : nb);
+      cp_async_zfill(At + r * kUpCols + c, nb ? a + (size_t)gr * n + cbase + c : a, 16, nb);
+    }
+  };
+  const int ri = tid >> 4, ci = tid & 15;  // 16 row groups of MR, 16 column groups of 4 + 4
+  issue_v(0, b0);
+  cp_async_commit();
+  for (int b = b0; b < b1; ++b) {
+    const int buf = (b - b0) & 1;
+    __syncthreads();  // epilogue b-1 done with At, FMA loop b-1 done with the other V buffer
+    issue_a(b);
+    if (b + 1 < b1) issue_v(buf ^ 1, b + 1);
+    cp_async_commit();
+    cp_async_wait<1>();  // V(b) has landed
+    __syncthreads();
+    T* Vb = Vt + buf * (kPB * RT);
+    if (b == 0) {  // rows crossing the panel's diagonal block: unit diagonal, zeros above
+      for (int e = tid; e < kPB * kPB; e += 256) {
+        const int k = e / kPB, r = e % kPB, gr = j0 + r;
+        T* p = Vb + k * RT + (r ^ up_swz(k));
+        *p = gr < m ? vmask<T>(*p, gr, j0, k) : T(0);
+      }
+      __syncthreads();
+    }
+    T acc[MR][8];
+#pragma unroll
+    for (int p = 0; p < MR; ++p)
+#pragma unroll
+      for (int q = 0; q < 8; ++q) acc[p][q] = T(0);
+#pragma unroll 8
+    for (int k = 0; k < kPB; ++k) {
+      T v[MR], w[8];
+#pragma unroll
+      for (int h = 0; h < MR / 4; ++h) lds4<T>(Vb + k * RT + ((MR * ri + 4 * h) ^ up_swz(k)), v + 4 * h);
+      lds4<T>(Ws + k * kUpCols + 4 * ci, w);
+      lds4<T>(Ws + k * kUpCols + 64 + 4 * ci, w + 4);
+#pragma unroll
+      for (int p = 0; p < MR; ++p)
+#pragma unroll
+        for (int q = 0; q < 8; ++q) acc[p][q] = fma_(v[p], w[q], acc[p][q]);
+    }
+    cp_async_wait<0>();  // A2 tile of this block (and V of the next) have landed
+    __syncthreads();
+    const int rb = j0 + b * RT;
+#pragma unroll
+    for (int p = 0; p < MR; ++p) {
+      const int gr = rb + MR * ri + p;
+      if (gr >= m) continue;
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int cc = 64 * h + 4 * ci;
+        if (cc >= cw) continue;
+        T t[4];
+        lds4<T>(At + (MR * ri + p) * kUpCols + cc, t);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) t[e] = t[e] - acc[p][4 * h + e];
+        using VT = typename V16K<T>::type;
+#pragma unroll
+        for (int u = 0; u < 4 / V; ++u)  // cw is a multiple of V here: 16-byte pieces are all-or-nothing
+          if (cc + u * V < cw)
+            reinterpret_cast<VT*>(a + (size_t)gr * n + cbase + cc)[u] = reinterpret_cast<const VT*>(t)[u];
       }
     }
   }
@@ -424,9 +765,9 @@ __global__ void __launch_bounds__(1024) qr_rsolve_kernel(const T* __restrict__ a
 // ------------------------------------------------------------------ host side ----
 template <typename T>
 struct QrLargePlan {
-  int nb, rows_cta;
-  size_t smem_panel, smem_apply, ws_bytes, wp_off, w2_off, t_off, gpart_off, y_off;
-  int ngroups, in_smem;
+  int nb, nb_panel, rows_cta;
+  size_t smem_panel, smem_apply, ws_bytes, wp_off, w2_off, t_off, gpart_off, gfull_off, y_off;
+  int ngroups, in_smem, in_smem_apply;
   bool ok;
 };
 
@@ -436,16 +777,23 @@ QrLargePlan<T> qr_large_plan(int m, int n) {
   pl.nb = grid_blocks();
   const int per = (((m + pl.nb - 1) / pl.nb) + 3) & ~3;
   pl.rows_cta = per;
-  const size_t fixed_panel = (96 + kGridMaxK + 64 + 32 + 2 * kPB * kPB + 8 * 32) * sizeof(T);
+  const size_t fixed_panel = (size_t)PanelCfg<T>::fixed_elems * sizeof(T);
   const size_t fixed_apply = (96 + kGridMaxK + 8) * sizeof(T);
+  // The panel kernel runs one 512-thread CTA per SM and keeps the first RR * 16 rows of a CTA in
+  // registers; the apply kernel runs 2 CTAs per SM.  Row blocks go to shared memory only if they fit.
+  pl.nb_panel = pl.nb / kGridCtasPerSm;
+  const int per_panel = (((m + pl.nb_panel - 1) / pl.nb_panel) + 3) & ~3;
+  const int reg_rows = PanelCfg<T>::RR * kPanelWarps;
+  const size_t extra_bytes = (size_t)(per_panel > reg_rows ? per_panel - reg_rows : 0) * 33 * sizeof(T);
   const size_t rows_bytes = (size_t)per * 33 * sizeof(T);
-  // both cooperative kernels run 2 CTAs per SM; the row block goes to shared memory only if it fits
-  pl.in_smem = (fixed_panel + rows_bytes) * kGridCtasPerSm <= 220 * 1024;
-  pl.smem_panel = fixed_panel + (pl.in_smem ? rows_bytes : 0);
-  pl.smem_apply = fixed_apply + (pl.in_smem ? rows_bytes : 0);
-  pl.ngroups = 32;
+  pl.in_smem = fixed_panel + extra_bytes <= 215 * 1024;
+  pl.in_smem_apply = (fixed_apply + rows_bytes) * kGridCtasPerSm <= 220 * 1024;
+  pl.smem_panel = fixed_panel + (pl.in_smem ? extra_bytes : 0);
+  pl.smem_apply = fixed_apply + (pl.in_smem_apply ? rows_bytes : 0);
+  pl.ngroups = kW2MaxGroups;  // upper bound; the launch picks the count per panel
   size_t off = grid_part_elems();
   pl.gpart_off = off; off += (size_t)pl.nb * kPB * kPB;
+  pl.gfull_off = off; off += kPB * kPB;
   pl.t_off = off; off += kPB * kPB;
   pl.wp_off = off; off += (size_t)pl.ngroups * kPB * pad4(n);
   pl.w2_off = off; off += (size_t)kPB * pad4(n);
@@ -463,36 +811,58 @@ int qr_large_factor(const T* A, T* a, T* taus, int m, int n, void* ws, size_t ws
   T* w = reinterpret_cast<T*>(ws);
   LXB_CUDA_TRY(cudaMemcpyAsync(a, A, (size_t)m * n * sizeof(T), cudaMemcpyDeviceToDevice, st));
   count_launch();
-  auto pk = qr_panel_kernel<T>;
+  auto pk = pl.in_smem ? qr_panel_kernel<T, true> : qr_panel_kernel<T, false>;
   LXB_CUDA_TRY(cudaFuncSetAttribute(pk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem_panel));
   int occ = 0;
-  LXB_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, pk, kGridThreads, pl.smem_panel));
-  if (occ * kNumSMs < pl.nb) return LXB_E_UNSUPPORTED;
+  LXB_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, pk, kPanelThreads, pl.smem_panel));
+  if (occ * kNumSMs < pl.nb_panel) return LXB_E_UNSUPPORTED;
   T* part = w;
   T* gpart = w + pl.gpart_off;
+  T* gfull = w + pl.gfull_off;
   T* Tm = w + pl.t_off;
   T* Wp = w + pl.wp_off;
   T* W2 = w + pl.w2_off;
   for (int j0 = 0; j0 < n; j0 += kPB) {
     int nbw = n - j0 < kPB ? n - j0 : kPB;
-    int mm = m, nn = n, jj0 = j0, ism = pl.in_smem;
-    void* args[] = {&a, &taus, &Tm, &part, &gpart, &mm, &nn, &jj0, &nbw, &ism};
-    LXB_CUDA_TRY(cudaLaunchCooperativeKernel((const void*)pk, dim3(pl.nb), dim3(kGridThreads), args,
+    int mm = m, nn = n, jj0 = j0;
+    void* args[] = {&a, &taus, &Tm, &part, &gpart, &gfull, &mm, &nn, &jj0, &nbw};
+    LXB_CUDA_TRY(cudaLaunchCooperativeKernel((const void*)pk, dim3(pl.nb_panel), dim3(kPanelThreads), args,
                                              pl.smem_panel, st));
     count_launch();
     const int ncols = n - j0 - kPB;
     if (ncols <= 0) break;
-    const int tiles = (ncols + 127) / 128;
+    const int tiles = (ncols + kUpCols - 1) / kUpCols;
     const int wtiles = (ncols + kW2Tile - 1) / kW2Tile;
-    int ngroups = pl.ngroups;
-    const size_t w_smem = (size_t)(32 * kPB + 32 * kW2Tile) * sizeof(T);
+    // row groups: about two waves of CTAs at the kernel's occupancy, whatever the tile count is
+    const int wocc = sizeof(T) == 4 ? 4 : 2;
+    int ngroups = (2 * wocc * kNumSMs + wtiles - 1) / wtiles;
+    ngroups = ngroups < 16 ? 16 : (ngroups > kW2MaxGroups ? kW2MaxGroups : ngroups);
+    const size_t w_smem = (size_t)kW2Stages * kW2Rows * (kPB + kW2Tile) * sizeof(T);
     LXB_CUDA_TRY(cudaFuncSetAttribute(qr_wpartial_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)w_smem));
-    qr_wpartial_kernel<T><<<dim3(wtiles, ngroups), 256, w_smem, st>>>(a, Wp, m, n, j0, ncols, ngroups);
+    qr_wpartial_kernel<T><<<dim3(wtiles, ngroups), kW2Threads, w_smem, st>>>(a, Wp, m, n, j0, ncols, ngroups);
     LXB_CUDA_CHECK_LAUNCH();
-    qr_wfinish_kernel<T><<<(ncols + 255) / 256, 256, 0, st>>>(Wp, Tm, W2, ncols, ngroups);
+    qr_wfinish_kernel<T><<<(ncols + kWfCols - 1) / kWfCols, 256, 0, st>>>(Wp, Tm, W2, ncols, ngroups);
     LXB_CUDA_CHECK_LAUNCH();
-    const int rblocks = (m - j0 + 63) / 64;
-    qr_update_kernel<T><<<dim3(tiles, rblocks), 256, 0, st>>>(a, W2, m, n, j0, ncols);
+    constexpr int V = 16 / (int)sizeof(T);
+    if ((n % V == 0) && ((reinterpret_cast<uintptr_t>(a) & 15) == 0)) {
+      constexpr int RT = UpCfg<T>::RT;
+      const int rblocks = (m - j0 + RT - 1) / RT;
+      // about four waves of CTAs (for balance); every CTA walks `per_strip` row blocks of its tile
+      int strips = (4 * (sizeof(T) == 4 ? 2 : 1) * kNumSMs + tiles - 1) / tiles;
+      strips = strips < 1 ? 1 : (strips > rblocks ? rblocks : strips);
+      const int per_strip = (rblocks + strips - 1) / strips;
+      strips = (rblocks + per_strip - 1) / per_strip;
+      LXB_CUDA_TRY(cudaFuncSetAttribute(qr_update_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        (int)UpCfg<T>::smem));
+      qr_update_kernel<T><<<dim3(tiles, strips), 256, UpCfg<T>::smem, st>>>(a, W2, m, n, j0, ncols, rblocks,
+                                                                            per_strip);
+    } else {
+      const int rblocks = (m - j0 + kUpRows - 1) / kUpRows;
+      const size_t u_smem = (size_t)(kPB * kUpLd + kPB * kUpCols) * sizeof(T);
+      LXB_CUDA_TRY(cudaFuncSetAttribute(qr_update_simple_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        (int)u_smem));
+      qr_update_simple_kernel<T><<<dim3(tiles, rblocks), 256, u_smem, st>>>(a, W2, m, n, j0, ncols);
+    }
     LXB_CUDA_CHECK_LAUNCH();
   }
   return 0;
@@ -512,7 +882,7 @@ int qr_large_solve(const T* a, const T* taus, const T* b, T* x, int m, int n, vo
   count_launch();
   auto ak = qr_apply_qt_kernel<T>;
   LXB_CUDA_TRY(cudaFuncSetAttribute(ak, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem_apply));
-  int mm = m, nn = n, ism = pl.in_smem;
+  int mm = m, nn = n, ism = pl.in_smem_apply;
   void* args[] = {&a, &taus, &y, &part, &mm, &nn, &ism};
   LXB_CUDA_TRY(cudaLaunchCooperativeKernel((const void*)ak, dim3(pl.nb), dim3(kGridThreads), args,
                                            pl.smem_apply, st));
@@ -527,6 +897,17 @@ int qr_large_solve(const T* a, const T* taus, const T* b, T* x, int m, int n, vo
 
 template <typename T>
 size_t qr_large_ws_bytes(int m, int n) { return qr_large_plan<T>(m, n).ws_bytes; }
+
+#ifdef LXB_QR_PROF
+}  // namespace lxb
+extern "C" void lxb_debug_qr_prof(unsigned long long* out) {
+  cudaDeviceSynchronize();
+  cudaMemcpyFromSymbol(out, lxb::g_prof, sizeof(lxb::g_prof));
+  unsigned long long z[16] = {0};
+  cudaMemcpyToSymbol(lxb::g_prof, z, sizeof(z));
+}
+namespace lxb {
+#endif
 
 #define LXB_INST_QRL(T)                                                                             \
   template int qr_large_factor<T>(const T*, T*, T*, int, int, void*, size_t, cudaStream_t);         \
