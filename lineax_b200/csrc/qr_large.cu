@@ -699,64 +699,192 @@ __global__ void __launch_bounds__(256, sizeof(T) == 4 ? 2 : 1)
 }
 
 // --------------------------------------------------- apply Q^T to one vector ----
-// y <- H_n ... H_2 H_1 y, panel by panel with the panel rows in shared memory (cooperative).
+// y <- H_n ... H_2 H_1 y, one 32-reflector block at a time with TWO grid barriers per block
+// (instead of one per reflector).  For block V (unit lower trapezoidal, taus t):
+//   pass A: every CTA accumulates G = V^T V (32 x 32) and w = V^T y over its rows,
+//   two-level deterministic sum over the CTAs,
+//   one warp runs the 32-step recurrence d_i = w_i, z_i = t_i d_i, w_j -= z_i G[i][j] (j > i),
+//           which is exactly applying H_1 .. H_32 in order,
+//   pass B: y -= V z.
+// Rows are partitioned once over [0, m) (a CTA's rows above the block's diagonal just sit out),
+// so y never migrates between CTAs.
+constexpr int kApElems = kPB * kPB + kPB;  // G and w
+__device__ __forceinline__ int ap_swz(int r) { return (r & 7) << 2; }
+
 template <typename T>
-__global__ void __launch_bounds__(kGridThreads)
+__global__ void __launch_bounds__(kPanelThreads, 1)
     qr_apply_qt_kernel(const T* __restrict__ a, const T* __restrict__ taus, T* __restrict__ y,
-                       T* __restrict__ part, int m, int n, int in_smem) {
+                       T* __restrict__ gpart, T* __restrict__ gfull, int m, int n) {
+  constexpr int nw = kPanelWarps;
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  T* red = reinterpret_cast<T*>(smem_raw);
-  T* vals = red + 96 + kGridMaxK;  // 1
-  T* P = vals + 8;                 // rows_cta x 33
-  GridTeam<T> team(part, red);
-  const int tid = team.tid, nt = team.nt;
+  T* Gs = reinterpret_cast<T*>(smem_raw);  // 1056: G and w
+  T* zs = Gs + kApElems;                   // 32
+  T* tiles = zs + kPB;                     // per warp: 32 x 32 row tile (XOR-swizzled) + 32 y values
+  cgx::grid_group grid = cgx::this_grid();
+  const int nb = gridDim.x, bid = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  T* tile = tiles + warp * (kPB * kPB + kPB);
+  T* ysm = tile + kPB * kPB;
+  const int per = (((m + nb - 1) / nb) + 3) & ~3;
+  const int lo = bid * per < m ? bid * per : m;
+  const int hi = lo + per < m ? lo + per : m;
   for (int j0 = 0; j0 < n; j0 += kPB) {
     const int nbw = min(kPB, n - j0);
-    int lo, hi;
-    team.slice(m - j0, lo, hi);
-    const int nrows = hi - lo;
-    if (in_smem) {
-      for (int idx = tid; idx < nrows * kPB; idx += nt) {
-        const int r = idx / kPB, c = idx % kPB;
-        P[r * 33 + c] = c < nbw ? vmask<T>(a[(size_t)(j0 + lo + r) * n + j0 + c], j0 + lo + r, j0, c) : T(0);
+    const bool cok = lane < nbw;
+    const int rs = lo > j0 ? lo : j0;
+    const int titers = hi > rs ? (hi - rs + 32 * nw - 1) / (32 * nw) : 0;  // block-uniform trip count
+    // a warp's 32-row tile: 32 independent 128-byte row loads in flight, then shared memory
+    auto load_tile = [&](int base) -> T {
+      T v[kPB];
+#pragma unroll
+      for (int rr = 0; rr < kPB; ++rr) {
+        const int r = base + rr;
+        v[rr] = (r < hi && cok) ? a[(size_t)r * n + j0 + lane] : T(0);
+      }
+      const T yv = base + lane < hi ? y[base + lane] : T(0);
+      __syncwarp();
+#pragma unroll
+      for (int rr = 0; rr < kPB; ++rr)
+        tile[rr * kPB + (lane ^ ap_swz(rr))] = (base + rr < hi && cok) ? vmask<T>(v[rr], base + rr, j0, lane) : T(0);
+      ysm[lane] = yv;
+      __syncwarp();
+      return yv;
+    };
+    // ---- pass A: lane c2 accumulates G[c1][c2] for all c1 (row entries broadcast 4 at a time)
+    T g[kPB];
+#pragma unroll
+    for (int c1 = 0; c1 < kPB; ++c1) g[c1] = T(0);
+    T wl = T(0);
+    for (int it = 0; it < titers; ++it) {
+      const int base = rs + (warp + it * nw) * 32;
+      load_tile(base);
+#pragma unroll 4
+      for (int rr = 0; rr < kPB; ++rr) {
+        const T x = tile[rr * kPB + (lane ^ ap_swz(rr))];
+        wl = fma_(x, ysm[rr], wl);
+#pragma unroll
+        for (int cg = 0; cg < kPB / 4; ++cg) {
+          T v4[4];
+          lds4<T>(tile + rr * kPB + ((4 * cg) ^ ap_swz(rr)), v4);
+#pragma unroll
+          for (int e = 0; e < 4; ++e) g[4 * cg + e] = fma_(v4[e], x, g[4 * cg + e]);
+        }
       }
     }
+    for (int e = tid; e < kApElems; e += kPanelThreads) Gs[e] = T(0);
     __syncthreads();
-    for (int jj = 0; jj < nbw; ++jj) {
-      T d[1] = {T(0)};
-      for (int r = tid; r < nrows; r += nt) {
-        const int gr = j0 + lo + r;
-        const T v = in_smem ? P[r * 33 + jj] : vmask<T>(a[(size_t)gr * n + j0 + jj], gr, j0, jj);
-        d[0] = fma_(v, y[gr], d[0]);
-      }
-      team.template reduce<1, 0>(d, nullptr);
-      const T f = taus[j0 + jj] * d[0];
-      for (int r = tid; r < nrows; r += nt) {
-        const int gr = j0 + lo + r;
-        const T v = in_smem ? P[r * 33 + jj] : vmask<T>(a[(size_t)gr * n + j0 + jj], gr, j0, jj);
-        y[gr] = fma_(-f, v, y[gr]);
+    for (int w = 0; w < nw; ++w) {
+      if (warp == w) {
+#pragma unroll
+        for (int c1 = 0; c1 < kPB; ++c1) Gs[c1 * kPB + lane] += g[c1];
+        Gs[kPB * kPB + lane] += wl;
       }
       __syncthreads();
     }
-    team.sync();  // rows are re-partitioned for the next panel
+    for (int e = tid; e < kApElems; e += kPanelThreads) gpart[(size_t)bid * kApElems + e] = Gs[e];
+    __threadfence();
+    grid.sync();
+    // ---- level 2: CTA b <= 32 sums row b of [G; w] over the CTAs
+    if (bid <= kPB) {
+      const int e0 = bid * kPB + warp * 2;
+      T s[2] = {T(0), T(0)};
+      for (int b = lane; b < nb; b += 32) {
+#pragma unroll
+        for (int u = 0; u < 2; ++u) s[u] += __ldcg(gpart + (size_t)b * kApElems + e0 + u);
+      }
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        const T t = warp_sum(s[u]);
+        if (lane == 0) gfull[e0 + u] = t;
+      }
+    }
+    __threadfence();
+    grid.sync();
+    for (int e = tid; e < kApElems; e += kPanelThreads) Gs[e] = __ldcg(gfull + e);
+    __syncthreads();
+    if (warp == 0) {
+      T w = Gs[kPB * kPB + lane];
+      const T tl = cok ? taus[j0 + lane] : T(0);
+#pragma unroll
+      for (int i = 0; i < kPB; ++i) {
+        const T zi = __shfl_sync(kFull, tl, i) * __shfl_sync(kFull, w, i);
+        if (lane == i) zs[i] = zi;
+        w = lane > i ? fma_(-zi, Gs[i * kPB + lane], w) : w;
+      }
+    }
+    __syncthreads();
+    // ---- pass B: lane = row of the tile, y_r -= sum_k v(r,k) z_k
+    T z[kPB];
+#pragma unroll
+    for (int cg = 0; cg < kPB / 4; ++cg) lds4<T>(zs + 4 * cg, z + 4 * cg);
+    for (int it = 0; it < titers; ++it) {
+      const int base = rs + (warp + it * nw) * 32;
+      const T yv = load_tile(base);
+      T acc = T(0);
+#pragma unroll
+      for (int cg = 0; cg < kPB / 4; ++cg) {
+        T v4[4];
+        lds4<T>(tile + lane * kPB + ((4 * cg) ^ ap_swz(lane)), v4);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) acc = fma_(v4[e], z[4 * cg + e], acc);
+      }
+      if (base + lane < hi) y[base + lane] = yv - acc;
+    }
+    __syncthreads();  // the row -> warp map shifts with j0
   }
 }
 
 // x = R^{-1} y[0:n] for the n x n upper-triangular R stored in `a` (row-major, ld n): one CTA,
-// column-oriented with the vector in shared memory.
+// blocked back substitution with the vector in shared memory.  Per 32-column block: warp 0 solves
+// the diagonal block with shuffles, then every thread owns whole rows above it and subtracts its
+// 32-term dot product (eight 128-bit loads per row, all rows of the block in flight together).
 template <typename T>
 __global__ void __launch_bounds__(1024) qr_rsolve_kernel(const T* __restrict__ a, const T* __restrict__ y,
                                                          T* __restrict__ x, int n) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  T* s = reinterpret_cast<T*>(smem_raw);
-  const int tid = threadIdx.x, nt = blockDim.x;
+  T* s = reinterpret_cast<T*>(smem_raw);  // n
+  __shared__ T Rb[kPB][kPB + 1];
+  const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, warp = tid >> 5;
+  constexpr int V = 16 / sizeof(T);
+  using VT = typename V16K<T>::type;
+  const bool al = (n % V == 0) && ((reinterpret_cast<uintptr_t>(a) & 15) == 0);
   for (int i = tid; i < n; i += nt) s[i] = y[i];
-  __syncthreads();
-  for (int k = n - 1; k >= 0; --k) {
-    if (tid == 0) s[k] = s[k] / a[(size_t)k * n + k];
+  const int nblk = (n + kPB - 1) / kPB;
+  for (int kb = nblk - 1; kb >= 0; --kb) {
+    const int k0 = kb * kPB, bw = min(kPB, n - k0);
+    for (int e = tid; e < kPB * kPB; e += nt) {
+      const int i = e / kPB, j = e % kPB;
+      Rb[i][j] = (i < bw && j < bw) ? a[(size_t)(k0 + i) * n + k0 + j] : T(i == j);
+    }
     __syncthreads();
-    const T xk = s[k];
-    for (int i = tid; i < k; i += nt) s[i] = fma_(-a[(size_t)i * n + k], xk, s[i]);
+    if (warp == 0) {
+      T xi = lane < bw ? s[k0 + lane] : T(0);
+#pragma unroll
+      for (int j = kPB - 1; j >= 0; --j) {
+        if (lane == j) xi = xi / Rb[j][j];
+        const T xj = __shfl_sync(kFull, xi, j);
+        if (lane < j) xi = fma_(-Rb[lane][j], xj, xi);
+      }
+      if (lane < bw) s[k0 + lane] = xi;
+    }
+    __syncthreads();
+    for (int i = tid; i < k0; i += nt) {
+      const T* row = a + (size_t)i * n + k0;
+      T acc = T(0);
+      if (al && bw == kPB) {
+        VT v[kPB / V];
+#pragma unroll
+        for (int u = 0; u < kPB / V; ++u) v[u] = reinterpret_cast<const VT*>(row)[u];
+#pragma unroll
+        for (int u = 0; u < kPB / V; ++u) {
+          const T* pv = reinterpret_cast<const T*>(&v[u]);
+#pragma unroll
+          for (int e = 0; e < V; ++e) acc = fma_(pv[e], s[k0 + u * V + e], acc);
+        }
+      } else {
+        for (int j = 0; j < bw; ++j) acc = fma_(row[j], s[k0 + j], acc);
+      }
+      s[i] = s[i] - acc;
+    }
     __syncthreads();
   }
   for (int i = tid; i < n; i += nt) x[i] = s[i];
@@ -766,8 +894,8 @@ __global__ void __launch_bounds__(1024) qr_rsolve_kernel(const T* __restrict__ a
 template <typename T>
 struct QrLargePlan {
   int nb, nb_panel, rows_cta;
-  size_t smem_panel, smem_apply, ws_bytes, wp_off, w2_off, t_off, gpart_off, gfull_off, y_off;
-  int ngroups, in_smem, in_smem_apply;
+  size_t smem_panel, ws_bytes, wp_off, w2_off, t_off, gpart_off, gfull_off, y_off;
+  int ngroups, in_smem;
   bool ok;
 };
 
@@ -778,22 +906,18 @@ QrLargePlan<T> qr_large_plan(int m, int n) {
   const int per = (((m + pl.nb - 1) / pl.nb) + 3) & ~3;
   pl.rows_cta = per;
   const size_t fixed_panel = (size_t)PanelCfg<T>::fixed_elems * sizeof(T);
-  const size_t fixed_apply = (96 + kGridMaxK + 8) * sizeof(T);
   // The panel kernel runs one 512-thread CTA per SM and keeps the first RR * 16 rows of a CTA in
-  // registers; the apply kernel runs 2 CTAs per SM.  Row blocks go to shared memory only if they fit.
+  // registers; the remaining rows go to shared memory only if they fit.
   pl.nb_panel = pl.nb / kGridCtasPerSm;
   const int per_panel = (((m + pl.nb_panel - 1) / pl.nb_panel) + 3) & ~3;
   const int reg_rows = PanelCfg<T>::RR * kPanelWarps;
   const size_t extra_bytes = (size_t)(per_panel > reg_rows ? per_panel - reg_rows : 0) * 33 * sizeof(T);
-  const size_t rows_bytes = (size_t)per * 33 * sizeof(T);
   pl.in_smem = fixed_panel + extra_bytes <= 215 * 1024;
-  pl.in_smem_apply = (fixed_apply + rows_bytes) * kGridCtasPerSm <= 220 * 1024;
   pl.smem_panel = fixed_panel + (pl.in_smem ? extra_bytes : 0);
-  pl.smem_apply = fixed_apply + (pl.in_smem_apply ? rows_bytes : 0);
   pl.ngroups = kW2MaxGroups;  // upper bound; the launch picks the count per panel
   size_t off = grid_part_elems();
   pl.gpart_off = off; off += (size_t)pl.nb * kPB * kPB;
-  pl.gfull_off = off; off += kPB * kPB;
+  pl.gfull_off = off; off += kPB * kPB + 2 * kPB;
   pl.t_off = off; off += kPB * kPB;
   pl.wp_off = off; off += (size_t)pl.ngroups * kPB * pad4(n);
   pl.w2_off = off; off += (size_t)kPB * pad4(n);
@@ -876,16 +1000,18 @@ int qr_large_solve(const T* a, const T* taus, const T* b, T* x, int m, int n, vo
   if (!pl.ok) return LXB_E_UNSUPPORTED;
   if (!ws || ws_bytes < pl.ws_bytes) return LXB_E_WORKSPACE;
   T* w = reinterpret_cast<T*>(ws);
-  T* part = w;
   T* y = w + pl.y_off;
   LXB_CUDA_TRY(cudaMemcpyAsync(y, b, (size_t)m * sizeof(T), cudaMemcpyDeviceToDevice, st));
   count_launch();
   auto ak = qr_apply_qt_kernel<T>;
-  LXB_CUDA_TRY(cudaFuncSetAttribute(ak, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem_apply));
-  int mm = m, nn = n, ism = pl.in_smem_apply;
-  void* args[] = {&a, &taus, &y, &part, &mm, &nn, &ism};
-  LXB_CUDA_TRY(cudaLaunchCooperativeKernel((const void*)ak, dim3(pl.nb), dim3(kGridThreads), args,
-                                           pl.smem_apply, st));
+  T* gpart = w + pl.gpart_off;  // nb x 1024 elements reserved, 148 x 1056 used
+  T* gfull = w + pl.gfull_off;
+  int mm = m, nn = n;
+  void* args[] = {&a, &taus, &y, &gpart, &gfull, &mm, &nn};
+  const size_t ap_smem = (size_t)(kApElems + kPB + kPanelWarps * (kPB * kPB + kPB)) * sizeof(T);
+  LXB_CUDA_TRY(cudaFuncSetAttribute(ak, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ap_smem));
+  LXB_CUDA_TRY(cudaLaunchCooperativeKernel((const void*)ak, dim3(pl.nb_panel), dim3(kPanelThreads), args, ap_smem,
+                                           st));
   count_launch();
   const size_t smem = (size_t)n * sizeof(T);
   if (smem > 200 * 1024) return LXB_E_UNSUPPORTED;
