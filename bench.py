@@ -157,7 +157,7 @@ def run_reference(args):
 def run_large(args, w, rank, local_rank, world):
     """Single large systems (BASELINE configs[3], configs[4]).  gmres32k with N > 1: ONE system
     row-sharded over the ranks (strong scaling, exchanges fused into the kernel over NVLink);
-    lsmr262k with N > 1: every rank solves its own replica."""
+    lsmr262k with N > 1: ONE tall system row-sharded the same way; qr262k / tridiag512: replicas."""
     import torch
     import torch.distributed as dist
 
@@ -168,12 +168,30 @@ def run_large(args, w, rank, local_rank, world):
     m = w.get("m", n)
     g = torch.Generator(device="cuda").manual_seed(rank)
     force = os.environ.get("LXB_FORCE_SHARDED") == "1"  # experiment: dist kernel on a 1-rank group
-    sharded = args.workload == "gmres32k" and (world > 1 or force)
+    sharded = args.workload in ("gmres32k", "lsmr262k") and (world > 1 or force)
     if force and world == 1 and not dist.is_initialized():
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         os.environ.setdefault("MASTER_PORT", "29577")
         dist.init_process_group("nccl", rank=0, world_size=1, device_id=torch.device("cuda", local_rank))
-    if sharded:
+    if sharded and args.workload == "lsmr262k":
+        # ONE tall system row-partitioned over the ranks; the A^T u all-reduce is fused in the kernel
+        from lineax_b200.distributed import RowShardedLSMR
+
+        solver = RowShardedLSMR(m, n, 1e-6, 1e-6, dtype=torch.float32)
+        lo, hi = solver.row_range()
+        A = torch.randn(hi - lo, n, generator=g, device="cuda", dtype=torch.float32) / (m ** 0.5)
+        gx = torch.Generator(device="cuda").manual_seed(12345)
+        xt = torch.randn(n, generator=gx, device="cuda", dtype=torch.float32)
+        b = _ops.matvec(A, xt, False) + 0.1 * torch.randn(hi - lo, generator=g, device="cuda", dtype=torch.float32)
+        m = hi - lo
+
+        def solve():
+            x, r, k, _ = solver.solve(A, b)
+            return x, r.reshape(1), k.reshape(1)
+
+        n_mv = lambda k: 2 + 2 * k
+        kernel_name = "lsmr_dist_kernel<float>"
+    elif sharded:
         # ONE system row-partitioned over the ranks (strong scaling); exchanges fused in the kernel
         from lineax_b200.distributed import RowShardedGMRES
 

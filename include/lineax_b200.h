@@ -231,6 +231,27 @@ LXB_DECL_VEC(f64, double)
 LXB_DECL_GMRES_DIST(f32, float)
 LXB_DECL_GMRES_DIST(f64, double)
 
+/* LSMR (lineax/_solver/lsmr.py:94-409) on ONE tall system partitioned by ROWS over the GPUs of an
+ * NVLink box: rank r owns m_local contiguous rows of A (A_local[m_local, n] row-major, 16-byte
+ * aligned) and the same slice of b; the solution x[n] and the statistics are replicated (every
+ * rank passes its own full-length x; with LXB_HAS_Y0 it holds the same y0 on every rank).  Each
+ * iteration reads the local rows once and does one in-kernel exchange over peer memory (all-reduce
+ * of the n partial column sums of A^T u and of ||u||^2).  Requires n to be a multiple of 16 bytes
+ * worth of elements and n <= 8192 (f32) / 4096 (f64); otherwise LXB_E_UNSUPPORTED.
+ * peer_buffers: as for GMRES, lxb_lsmr_rowsharded_symm_bytes_* bytes per rank.
+ */
+#define LXB_DECL_LSMR_DIST(sfx, T)                                                                  \
+  int lxb_lsmr_rowsharded_##sfx(const T* A_local, const T* b_local, T* x, int32_t* result,         \
+                                int32_t* num_steps, T* stats, int32_t m, int32_t m_local,          \
+                                int32_t n, T rtol, T atol, T conlim, int64_t max_steps,            \
+                                int32_t flags, void* workspace, size_t workspace_bytes,            \
+                                void* const* peer_buffers, int32_t world, int32_t rank,            \
+                                lxb_stream_t stream);                                              \
+  size_t lxb_lsmr_rowsharded_workspace_##sfx(int32_t m_local, int32_t n);                          \
+  size_t lxb_lsmr_rowsharded_symm_bytes_##sfx(int32_t n, int32_t world);
+LXB_DECL_LSMR_DIST(f32, float)
+LXB_DECL_LSMR_DIST(f64, double)
+
 /* ------------------------------------------------------ post-processing --
  * lineax/_solve.py:104-123, per system:
  *   successful & any(!isfinite(x)) -> singular;  singular & any(!isfinite(b)) -> nonfinite_input.

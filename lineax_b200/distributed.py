@@ -1,9 +1,10 @@
 """Row-sharded solves of ONE large system across the GPUs of an NVLink box.
 
 One process per GPU (`torch.distributed`, NCCL for the rendezvous only).  The data-path exchanges
-(all-gather of the Krylov vector, all-reduce of the Gram-Schmidt scalars) are NOT NCCL calls: they
-are fused into the persistent solver kernel over peer memory obtained from
-`torch.distributed._symmetric_memory` (csrc/gmres_dist.cu).
+(GMRES: all-gather of the Krylov vector, all-reduce of the Gram-Schmidt scalars; LSMR: all-reduce of
+the partial `A^T u` and of `||u||^2`) are NOT NCCL calls: they are fused into the persistent solver
+kernels over peer memory obtained from `torch.distributed._symmetric_memory`
+(csrc/gmres_dist.cu, csrc/lsmr_dist.cu).
 """
 from __future__ import annotations
 
@@ -68,3 +69,68 @@ class RowShardedGMRES:
                  self.stagnation_iters, flags, ws.data_ptr(), ws_bytes, self.peers_dev, self.world, self.rank,
                  torch.cuda.current_stream().cuda_stream)
         return x, result[0], steps[0]
+
+
+class RowShardedLSMR:
+    """LSMR (lineax/_solver/lsmr.py semantics) on a tall dense operator partitioned by ROWS.
+
+    Every rank constructs it with the same arguments and then calls `solve(A_local, b_local)` with
+    its contiguous block of rows (`row_range(rank)`); returns `(x, result, num_steps, stats)` where
+    the length-`n` solution and the statistics (same keys as `lineax_b200.LSMR`) are replicated
+    bit-identically on every rank.
+    """
+
+    def __init__(self, m: int, n: int, rtol: float, atol: float, *, conlim: float = 1e8, max_steps=None,
+                 dtype=torch.float32, group=None):
+        import torch.distributed._symmetric_memory as symm
+
+        self.m, self.n, self.rtol, self.atol = int(m), int(n), float(rtol), float(atol)
+        self.conlim, self.max_steps = float(conlim), max_steps
+        self.dtype, self.group = dtype, group if group is not None else dist.group.WORLD
+        self.world, self.rank = dist.get_world_size(self.group), dist.get_rank(self.group)
+        self.bounds = shard_bounds(self.m, self.world)
+        self.sfx = nat.suffix(dtype)
+        self.device = torch.device("cuda", torch.cuda.current_device())
+        nbytes = nat.fn(f"lxb_lsmr_rowsharded_symm_bytes_{self.sfx}")(self.n, self.world)
+        self.symm_buf = symm.empty(nbytes, dtype=torch.uint8, device=self.device)
+        self.symm_buf.zero_()
+        self.handle = symm.rendezvous(self.symm_buf, self.group)
+        self.peers_dev = int(self.handle.buffer_ptrs_dev)
+        torch.cuda.synchronize()
+        dist.barrier(self.group)  # every rank's flags are zero before the first kernel starts
+
+    def row_range(self, rank=None):
+        r = self.rank if rank is None else rank
+        return self.bounds[r], self.bounds[r + 1]
+
+    def solve(self, a_local: torch.Tensor, b_local: torch.Tensor, y0: torch.Tensor | None = None):
+        lo, hi = self.row_range()
+        ml = hi - lo
+        if tuple(a_local.shape) != (ml, self.n) or tuple(b_local.shape) != (ml,):
+            raise ValueError(f"rank {self.rank}: expected A_local {(ml, self.n)} and b_local {(ml,)}")
+        a_local = a_local.to(self.dtype).contiguous()
+        b_local = b_local.to(self.dtype).contiguous()
+        min_dim = min(self.m, self.n)
+        flags = 0
+        if self.max_steps is None:  # lsmr.py:121-129, with the integer-overflow guard
+            imax = torch.iinfo(torch.int32 if self.dtype == torch.float32 else torch.int64).max
+            ms = imax if min_dim > imax / 10 else min_dim * 10
+        else:
+            ms, flags = int(self.max_steps), nat.MAXSTEPS_GIVEN
+        if y0 is not None:
+            x = y0.to(self.dtype).contiguous().clone()
+            flags |= nat.HAS_Y0
+        else:
+            x = torch.empty(self.n, dtype=self.dtype, device=self.device)
+        result = torch.empty(1, dtype=torch.int32, device=self.device)
+        steps = torch.empty(1, dtype=torch.int32, device=self.device)
+        st = torch.empty(8, dtype=self.dtype, device=self.device)
+        ws_bytes = nat.fn(f"lxb_lsmr_rowsharded_workspace_{self.sfx}")(ml, self.n)
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=self.device)
+        nat.call(f"lxb_lsmr_rowsharded_{self.sfx}", a_local.data_ptr(), b_local.data_ptr(), x.data_ptr(),
+                 result.data_ptr(), steps.data_ptr(), st.data_ptr(), self.m, ml, self.n, self.rtol, self.atol,
+                 self.conlim, ms, flags, ws.data_ptr(), ws_bytes, self.peers_dev, self.world, self.rank,
+                 torch.cuda.current_stream().cuda_stream)
+        stats = {"num_steps": steps[0], "istop": st[0].to(torch.int32), "norm_r": st[1], "norm_Ar": st[2],
+                 "norm_A": st[3], "cond_A": st[4], "norm_x": st[5]}
+        return x, result[0], steps[0], stats
