@@ -263,6 +263,10 @@ int gmres_dist_launch(const T* A_local, const T* b_local, T* x_local, int32_t* r
   if (occ < 1) return LXB_E_UNSUPPORTED;
   int nb = occ * sms;
   if (nb > grid_blocks()) nb = grid_blocks();
+  if (const char* e = getenv("LXB_MV_RB")) {
+    const int rb = atoi(e);
+    LXB_CUDA_TRY(cudaMemcpyToSymbolAsync(g_mv_force_rb, &rb, sizeof(int), 0, cudaMemcpyHostToDevice, st));
+  }
   void* args[] = {&dp};
   LXB_CUDA_TRY(cudaLaunchCooperativeKernel((const void*)kern, dim3(nb), dim3(kDistThreads), args, smem, st));
   count_launch();
