@@ -9,8 +9,9 @@
 //     K2 qr_wpartial_kernel: Wp[g] = V[rows_g]^T A2[rows_g]   (register-tiled, row groups)
 //     K3 qr_wfinish_kernel : W2 = T^T (sum_g Wp[g])
 //     K4 qr_update_kernel  : A2 -= V W2                        (register-tiled 64x128 tiles)
-// Everything is fp32/fp64 SIMT FMA: the 1e-5 parity budget rules out plain TF32 tensor-core
-// tiles (SURVEY.md section 7 "hard parts"); a split-precision tcgen05 trailing update is future work.
+// The 1e-5 parity budget rules out plain TF32 tensor-core tiles (SURVEY.md section 7 "hard parts"):
+// the fp32 update runs on tcgen05 with the 3xTF32 split (qr_update_tc_kernel), everything else is
+// fp32/fp64 SIMT FMA.
 #include "krylov_grid.cuh"
 #include "krylov_grid_api.cuh"
 
@@ -698,6 +699,193 @@ __global__ void __launch_bounds__(256, sizeof(T) == 4 ? 2 : 1)
   }
 }
 
+// Tensor-core variant of the update (fp32, aligned rows; the default there, LXB_QR_TC=0 turns it off):
+// P = V W on the 5th-generation tensor cores with the 3xTF32 split (x = hi + lo, hi = the 19 leading
+// bits; P = Vhi Whi + Vhi Wlo + Vlo Whi accumulated in fp32 in tensor memory), so the products keep
+// ~2^-21 relative accuracy instead of TF32's 2^-11.  One CTA of 4 warps owns a 128-column tile and
+// walks a strip of 128-row blocks:
+//   W tile  -> Bhi / Blo  (128 x 32, K-major, 128-byte swizzle; written once per CTA)
+//   V block -> Ahi / Alo  (128 x 32, same layout; thread t stages row t)
+//   one thread issues 12 tcgen05.mma (M = N = 128, K = 8) into 128 TMEM columns and commits to an
+//   mbarrier; every warp then reads its 32 TMEM lanes back (tcgen05.ld 32x32b.x32) and does the
+//   read-modify-write of A2, one 128-byte row segment per thread per 32-column chunk.
+namespace tc {
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+// K-major, SWIZZLE_128B operand tile with 128-byte rows: 8-row groups are 1024 bytes apart
+__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr) {
+  return (uint64_t)((saddr >> 4) & 0x3fffu) | ((uint64_t)1 << 16) | ((uint64_t)(1024 >> 4) << 32) |
+         ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
+}
+// kind::tf32, fp32 accumulate, A and B K-major, M = 128, N = 128
+constexpr uint32_t kIdesc = (1u << 4) | (2u << 7) | (2u << 10) | ((128u >> 3) << 17) | ((128u >> 4) << 24);
+__device__ __forceinline__ void mma_tf32(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(tmem_d),
+      "l"(da), "l"(db), "r"(kIdesc), "r"(accumulate)
+      : "memory");
+}
+// byte offset of the 16-byte chunk `c` (0..7) of row `r` inside a swizzled 128 x 32 fp32 tile
+__device__ __forceinline__ int sw128(int r, int c) { return (r >> 3) * 1024 + (r & 7) * 128 + ((c ^ (r & 7)) << 4); }
+__device__ __forceinline__ void split_store(unsigned char* hi, unsigned char* lo, int r, int c, float4 x) {
+  float4 h, l;
+  h.x = __uint_as_float(__float_as_uint(x.x) & 0xffffe000u); l.x = x.x - h.x;
+  h.y = __uint_as_float(__float_as_uint(x.y) & 0xffffe000u); l.y = x.y - h.y;
+  h.z = __uint_as_float(__float_as_uint(x.z) & 0xffffe000u); l.z = x.z - h.z;
+  h.w = __uint_as_float(__float_as_uint(x.w) & 0xffffe000u); l.w = x.w - h.w;
+  *reinterpret_cast<float4*>(hi + sw128(r, c)) = h;
+  *reinterpret_cast<float4*>(lo + sw128(r, c)) = l;
+}
+}  // namespace tc
+
+constexpr int kTcThreads = 128;
+constexpr size_t kTcSmem = 4 * 16384 + 1024 /* alignment slack */ + 64;
+
+__global__ void __launch_bounds__(kTcThreads)
+    qr_update_tc_kernel(float* __restrict__ a, const float* __restrict__ W2, int m, int n, int j0, int ncols,
+                        int rblocks, int per_strip, int* __restrict__ err) {
+  extern __shared__ unsigned char smem_dyn[];
+  unsigned char* base = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~(uintptr_t)1023);
+  unsigned char* Bhi = base;
+  unsigned char* Blo = base + 16384;
+  unsigned char* Ahi = base + 2 * 16384;
+  unsigned char* Alo = base + 3 * 16384;
+  uint64_t* mbar = reinterpret_cast<uint64_t*>(base + 4 * 16384);
+  uint32_t* tslot = reinterpret_cast<uint32_t*>(base + 4 * 16384 + 16);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int tile = blockIdx.x;
+  const int cbase = j0 + kPB + tile * 128;
+  const int cw = min(128, ncols - tile * 128);
+  const int b0 = blockIdx.y * per_strip, b1 = min(rblocks, b0 + per_strip);
+  if (b0 >= b1) return;  // uniform per CTA, before any allocation
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tc::smem_u32(tslot)), "r"(128));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  if (tid == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(tc::smem_u32(mbar)));
+    asm volatile("fence.mbarrier_init.release.cluster;");
+  }
+  // W tile: thread t owns column t (row t of the K-major B operand)
+  {
+    float w[kPB];
+#pragma unroll
+    for (int k = 0; k < kPB; ++k) w[k] = tid < cw ? W2[(size_t)k * ncols + tile * 128 + tid] : 0.f;
+#pragma unroll
+    for (int c = 0; c < 8; ++c) tc::split_store(Bhi, Blo, tid, c, make_float4(w[4 * c], w[4 * c + 1], w[4 * c + 2], w[4 * c + 3]));
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;");
+  const uint32_t tmem = *tslot;
+  const uint32_t a_hi = tc::smem_u32(Ahi), a_lo = tc::smem_u32(Alo), b_hi = tc::smem_u32(Bhi), b_lo = tc::smem_u32(Blo);
+  uint32_t phase = 0;
+  // The CTA is latency bound on its A2 read-modify-write (ncu: 12 warps per SM, long_scoreboard 18
+  // per issue), so every block's A2 tile and V rows are pulled into L2 one block ahead.
+  auto prefetch_block = [&](int bb) {
+    const int prb = j0 + bb * 128;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int line = tid + i * 128, r = line >> 2, seg = line & 3, gr = prb + r;  // 4 x 128-byte lines per row
+      if (gr < m && seg * 32 < cw) asm volatile("prefetch.global.L2 [%0];" ::"l"(a + (size_t)gr * n + cbase + seg * 32));
+    }
+    if (prb + tid < m) asm volatile("prefetch.global.L2 [%0];" ::"l"(a + (size_t)(prb + tid) * n + j0));
+  };
+  prefetch_block(b0);
+  for (int b = b0; b < b1; ++b) {
+    const int rb = j0 + b * 128;
+    if (b + 1 < b1) prefetch_block(b + 1);
+    {
+      // 8 lanes per row (one 16-byte chunk each), 16 rows per sweep: fully coalesced 128-byte rows
+      float4 v[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int r = (tid >> 3) + 16 * i, c = tid & 7, gr = rb + r;
+        v[i] = gr < m ? reinterpret_cast<const float4*>(a + (size_t)gr * n + j0)[c] : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int r = (tid >> 3) + 16 * i, c = tid & 7, gr = rb + r;
+        if (b == 0) {  // rows crossing the panel's diagonal block: unit diagonal, zeros above
+          v[i].x = vmask<float>(v[i].x, gr, j0, 4 * c);
+          v[i].y = vmask<float>(v[i].y, gr, j0, 4 * c + 1);
+          v[i].z = vmask<float>(v[i].z, gr, j0, 4 * c + 2);
+          v[i].w = vmask<float>(v[i].w, gr, j0, 4 * c + 3);
+        }
+        tc::split_store(Ahi, Alo, r, c, v[i]);
+      }
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> tensor-core reads
+    __syncthreads();
+    if (tid == 0) {
+      asm volatile("tcgen05.fence::after_thread_sync;");
+#pragma unroll
+      for (int ks = 0; ks < 4; ++ks) {  // K = 32 in steps of 8 tf32 = 32 bytes along the swizzled row
+        const uint64_t dah = tc::umma_desc(a_hi + 32 * ks), dal = tc::umma_desc(a_lo + 32 * ks);
+        const uint64_t dbh = tc::umma_desc(b_hi + 32 * ks), dbl = tc::umma_desc(b_lo + 32 * ks);
+        tc::mma_tf32(tmem, dal, dbh, ks > 0 ? 1u : 0u);  // small terms first
+        tc::mma_tf32(tmem, dah, dbl, 1u);
+        tc::mma_tf32(tmem, dah, dbh, 1u);
+      }
+      asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(tc::smem_u32(mbar)) : "memory");
+    }
+    {
+      uint32_t done = 0;
+      for (int spin = 0; spin < (1 << 22) && !done; ++spin)
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}\n"
+                     : "=r"(done) : "r"(tc::smem_u32(mbar)), "r"(phase) : "memory");
+      if (!done && tid == 0) atomicExch(err, 1);  // never hang the GPU: report and carry on
+      phase ^= 1;
+    }
+    asm volatile("tcgen05.fence::after_thread_sync;");
+    // Epilogue.  tcgen05.ld hands every thread 32 consecutive columns of ITS row; going to global
+    // memory like that would touch 32 different lines per instruction, so each warp turns its
+    // 32 x 32 chunk around in shared memory (the A tiles are dead once the MMAs have completed;
+    // 16-byte chunks XOR-swizzled by row) and does the read-modify-write with 8 lanes per row.
+    float4* S = reinterpret_cast<float4*>(Ahi + warp * 4096);  // 32 rows x 8 chunks
+#pragma unroll 1
+    for (int qc = 0; qc < 4; ++qc) {
+      uint32_t r[32];
+      const uint32_t taddr = tmem + ((uint32_t)(32 * warp) << 16) + 32 * qc;
+      asm volatile(
+          "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+          "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+          "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+          : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+            "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+            "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+            "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+          : "r"(taddr));
+      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+      __syncwarp();  // previous chunk's readers are done with S
+#pragma unroll
+      for (int g4 = 0; g4 < 8; ++g4)
+        S[lane * 8 + (g4 ^ (lane & 7))] = make_float4(__uint_as_float(r[4 * g4]), __uint_as_float(r[4 * g4 + 1]),
+                                                      __uint_as_float(r[4 * g4 + 2]), __uint_as_float(r[4 * g4 + 3]));
+      __syncwarp();
+      const int c = lane & 7, col = 32 * qc + 4 * c;
+      float4 x[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int rr = 4 * i + (lane >> 3), gr = rb + 32 * warp + rr;
+        if (gr < m && col < cw) x[i] = *reinterpret_cast<const float4*>(a + (size_t)gr * n + cbase + col);
+      }
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int rr = 4 * i + (lane >> 3), gr = rb + 32 * warp + rr;
+        if (gr < m && col < cw) {  // aligned rows: ncols (hence cw) is a multiple of 4
+          const float4 p = S[rr * 8 + (c ^ (rr & 7))];
+          x[i].x -= p.x; x[i].y -= p.y; x[i].z -= p.z; x[i].w -= p.w;
+          *reinterpret_cast<float4*>(a + (size_t)gr * n + cbase + col) = x[i];
+        }
+      }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;");
+    __syncthreads();  // TMEM and the A tiles are free for the next block
+  }
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(128));
+}
+
 // --------------------------------------------------- apply Q^T to one vector ----
 // y <- H_n ... H_2 H_1 y, one 32-reflector block at a time with TWO grid barriers per block
 // (instead of one per reflector).  For block V (unit lower trapezoidal, taus t):
@@ -968,7 +1156,19 @@ int qr_large_factor(const T* A, T* a, T* taus, int m, int n, void* ws, size_t ws
     qr_wfinish_kernel<T><<<(ncols + kWfCols - 1) / kWfCols, 256, 0, st>>>(Wp, Tm, W2, ncols, ngroups);
     LXB_CUDA_CHECK_LAUNCH();
     constexpr int V = 16 / (int)sizeof(T);
-    if ((n % V == 0) && ((reinterpret_cast<uintptr_t>(a) & 15) == 0)) {
+    // tensor-core update is the default for fp32; LXB_QR_TC=0 selects the plain fp32 FMA kernel
+    static const bool use_tc = [] { const char* e = getenv("LXB_QR_TC"); return !(e && atoi(e) == 0); }();
+    if (use_tc && sizeof(T) == 4 && (n % 4 == 0) && ((reinterpret_cast<uintptr_t>(a) & 15) == 0)) {
+      const int rblocks = (m - j0 + 127) / 128;
+      int strips = (4 * 3 * kNumSMs + tiles - 1) / tiles;
+      strips = strips < 1 ? 1 : (strips > rblocks ? rblocks : strips);
+      const int per_strip = (rblocks + strips - 1) / strips;
+      strips = (rblocks + per_strip - 1) / per_strip;
+      LXB_CUDA_TRY(cudaFuncSetAttribute(qr_update_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTcSmem));
+      int* errp = reinterpret_cast<int*>(w + pl.gfull_off + kPB * kPB + kPB);  // spare words after [G; w]
+      qr_update_tc_kernel<<<dim3(tiles, strips), kTcThreads, kTcSmem, st>>>(
+          reinterpret_cast<float*>(a), reinterpret_cast<const float*>(W2), m, n, j0, ncols, rblocks, per_strip, errp);
+    } else if ((n % V == 0) && ((reinterpret_cast<uintptr_t>(a) & 15) == 0)) {
       constexpr int RT = UpCfg<T>::RT;
       const int rblocks = (m - j0 + RT - 1) / RT;
       // about four waves of CTAs (for balance); every CTA walks `per_strip` row blocks of its tile
