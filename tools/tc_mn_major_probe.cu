@@ -181,6 +181,134 @@ __global__ void __launch_bounds__(128) control_kernel(const float* A, const floa
   if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(128));
 }
 
+// Candidate fix: keep BOTH operands K-major (the verified configuration) by transposing the chunks while staging.
+// Thread (rq = tid & 7, cq) loads a 4 x 4 block (rows 4rq.., columns 4cq..), transposes it in registers and stores
+// four 16-byte K-chunks (one per column); a quarter warp covers the 8 chunks of one tile row: conflict free.
+constexpr uint32_t kIdescKT = (1u << 4) | (2u << 7) | (2u << 10) | ((32u >> 3) << 17) | ((128u >> 4) << 24);
+__global__ void __launch_bounds__(128) probe_kernel_kt(const float* A2, int lda, const float* V, int ldv, float* W, int R,
+                                                       int* err) {
+  extern __shared__ unsigned char smem_dyn[];
+  unsigned char* base = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~(uintptr_t)1023);
+  unsigned char *Ahi = base, *Alo = base + 16384, *Bhi = base + 32768, *Blo = base + 36864;
+  uint64_t* mbar = reinterpret_cast<uint64_t*>(base + 40960);
+  uint32_t* tslot = reinterpret_cast<uint32_t*>(base + 40976);
+  const int tid = threadIdx.x, warp = tid >> 5;
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tslot)), "r"(32));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  if (tid == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(mbar)));
+    asm volatile("fence.mbarrier_init.release.cluster;");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;");
+  const uint32_t tmem = *tslot;
+  float acc[32];
+#pragma unroll
+  for (int k = 0; k < 32; ++k) acc[k] = 0.f;
+  uint32_t phase = 0;
+  const int rq = tid & 7;
+  for (int ch = 0; ch < R / 32; ++ch) {
+    const int rb = ch * 32;
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      const int cq = (tid >> 3) + 16 * i;
+      float4 x[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) x[j] = reinterpret_cast<const float4*>(A2 + (size_t)(rb + 4 * rq + j) * lda)[cq];
+      split_store(Ahi, Alo, 4 * cq + 0, rq, make_float4(x[0].x, x[1].x, x[2].x, x[3].x));
+      split_store(Ahi, Alo, 4 * cq + 1, rq, make_float4(x[0].y, x[1].y, x[2].y, x[3].y));
+      split_store(Ahi, Alo, 4 * cq + 2, rq, make_float4(x[0].z, x[1].z, x[2].z, x[3].z));
+      split_store(Ahi, Alo, 4 * cq + 3, rq, make_float4(x[0].w, x[1].w, x[2].w, x[3].w));
+    }
+    if (tid < 64) {
+      const int cq = tid >> 3;
+      float4 x[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) x[j] = reinterpret_cast<const float4*>(V + (size_t)(rb + 4 * rq + j) * ldv)[cq];
+      split_store(Bhi, Blo, 4 * cq + 0, rq, make_float4(x[0].x, x[1].x, x[2].x, x[3].x));
+      split_store(Bhi, Blo, 4 * cq + 1, rq, make_float4(x[0].y, x[1].y, x[2].y, x[3].y));
+      split_store(Bhi, Blo, 4 * cq + 2, rq, make_float4(x[0].z, x[1].z, x[2].z, x[3].z));
+      split_store(Bhi, Blo, 4 * cq + 3, rq, make_float4(x[0].w, x[1].w, x[2].w, x[3].w));
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    __syncthreads();
+    if (tid == 0) {
+      asm volatile("tcgen05.fence::after_thread_sync;");
+#pragma unroll
+      for (int ks = 0; ks < 4; ++ks) {
+        const uint64_t dah = desc_k(smem_u32(Ahi) + 32 * ks), dal = desc_k(smem_u32(Alo) + 32 * ks);
+        const uint64_t dbh = desc_k(smem_u32(Bhi) + 32 * ks), dbl = desc_k(smem_u32(Blo) + 32 * ks);
+        asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(tmem), "l"(dal), "l"(dbh), "r"(kIdescKT), "r"(ks > 0 ? 1u : 0u) : "memory");
+        asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(tmem), "l"(dah), "l"(dbl), "r"(kIdescKT), "r"(1u) : "memory");
+        asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(tmem), "l"(dah), "l"(dbh), "r"(kIdescKT), "r"(1u) : "memory");
+      }
+      asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(mbar)) : "memory");
+    }
+    uint32_t done = 0;
+    for (int spin = 0; spin < (1 << 22) && !done; ++spin)
+      asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}\n"
+                   : "=r"(done) : "r"(smem_u32(mbar)), "r"(phase) : "memory");
+    if (!done && tid == 0) atomicExch(err, 1);
+    phase ^= 1;
+    asm volatile("tcgen05.fence::after_thread_sync;");
+    uint32_t r[32];
+    const uint32_t taddr = tmem + ((uint32_t)(32 * warp) << 16);
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+          "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+          "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int k = 0; k < 32; ++k) acc[k] += __uint_as_float(r[k]);
+    asm volatile("tcgen05.fence::before_thread_sync;");
+    __syncthreads();
+  }
+#pragma unroll
+  for (int k = 0; k < 32; ++k) W[k * 128 + tid] = acc[k];
+  __syncthreads();
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(32));
+}
+
+static void run_kt() {
+  for (int R : {32, 64, 160, 512, 2048}) {
+    const int lda = 256, ldv = 64;
+    std::vector<float> A((size_t)R * lda), V((size_t)R * ldv), W(32 * 128);
+    srand(3);
+    for (auto& x : A) x = (rand() / (float)RAND_MAX - 0.5f) * 0.01f;
+    for (auto& x : V) x = (rand() / (float)RAND_MAX - 0.5f) * 0.01f;
+    for (int i = 0; i < 32; ++i) V[(size_t)i * ldv + i] = 1.f;
+    float *dA, *dV, *dW; int* derr;
+    cudaMalloc(&dA, A.size() * 4); cudaMalloc(&dV, V.size() * 4); cudaMalloc(&dW, W.size() * 4); cudaMalloc(&derr, 4);
+    cudaMemcpy(dA, A.data(), A.size() * 4, cudaMemcpyHostToDevice);
+    cudaMemcpy(dV, V.data(), V.size() * 4, cudaMemcpyHostToDevice);
+    cudaMemset(derr, 0, 4); cudaMemset(dW, 0xFF, W.size() * 4);
+    const size_t smem = 2 * 16384 + 2 * 4096 + 1024 + 64;
+    cudaFuncSetAttribute(probe_kernel_kt, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    probe_kernel_kt<<<1, 128, smem>>>(dA, lda, dV, ldv, dW, R, derr);
+    cudaError_t e = cudaGetLastError();
+    if (e == cudaSuccess) e = cudaDeviceSynchronize();
+    cudaMemcpy(W.data(), dW, W.size() * 4, cudaMemcpyDeviceToHost);
+    double maxerr = 0, maxref = 0;
+    for (int k = 0; k < 32; ++k)
+      for (int c = 0; c < 128; ++c) {
+        double s2 = 0;
+        for (int i = 0; i < R; ++i) s2 += (double)V[(size_t)i * ldv + k] * A[(size_t)i * lda + c];
+        maxerr = fmax(maxerr, fabs(s2 - W[k * 128 + c])); maxref = fmax(maxref, fabs(s2));
+      }
+    printf("transposed staging, K-major (R = %4d): cuda %s, max err %.3e (max |W| %.3e)\n", R, cudaGetErrorString(e), maxerr, maxref);
+    cudaFree(dA); cudaFree(dV); cudaFree(dW); cudaFree(derr);
+    if (e != cudaSuccess) break;
+  }
+}
+
 static void run_control() {
   std::vector<float> A(128 * 32), B(128 * 32), P(128 * 128);
   srand(2);
@@ -210,6 +338,7 @@ static void run_control() {
 
 int main() {
   run_control();
+  run_kt();
   struct Var { const char* name; uint32_t idesc, lbo, sbo, layout; };
   const uint32_t base = (1u << 4) | (2u << 7) | (2u << 10) | ((32u >> 3) << 17) | ((128u >> 4) << 24);
   const Var vars[] = {
