@@ -145,3 +145,103 @@ def test_row_sharded_lsmr_decomposition_world2_gloo(tmp_path):
     mp.spawn(_lsmr_rows_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
     x0, x1 = np.load(tmp_path / "lsmr0.npy"), np.load(tmp_path / "lsmr1.npy")
     assert np.array_equal(x0, x1)  # replicated state stays bit-identical: the all-reduce result is the same everywhere
+
+
+def _gmres_rows_worker(rank, world, port, out_dir):
+    """The decomposition gmres_dist.cu uses, restated with numpy + gloo: rank p owns a block of rows of A and the same
+    slice of every vector; per Arnoldi step an all-gather of the Krylov vector, ONE fused all-reduce of the restart + 1
+    Gram-Schmidt projections together with ||w||^2, one all-reduce for the new norm; max-norms by all-reduce(MAX)."""
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    import oracle
+    from oracle import gen
+    from oracle.direct import qr_compute, qr_init
+    from lineax_b200._shard import shard_bounds
+
+    n, tol, restart, stagnation_iters = 203, 1e-10, 20, 20
+    a, b, _ = gen.easy_problem(5, n, np.float64, spd=False)
+    bounds = shard_bounds(n, world)
+    lo, hi = bounds[rank], bounds[rank + 1]
+    al, bl = a[lo:hi], b[lo:hi]
+    eps = np.finfo(np.float64).eps
+
+    def allsum(vec):
+        t = torch.as_tensor(np.ascontiguousarray(np.atleast_1d(vec), dtype=np.float64))
+        dist.all_reduce(t)
+        return t.numpy()
+
+    def allmax(x):
+        t = torch.as_tensor(np.array([x], dtype=np.float64))
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def gather(vl):  # all-gather of a row-sharded vector (gloo wants equal sizes: pad to the largest shard)
+        width = max(bounds[r + 1] - bounds[r] for r in range(world))
+        mine = torch.zeros(width, dtype=torch.float64)
+        mine[: hi - lo] = torch.as_tensor(np.ascontiguousarray(vl))
+        parts = [torch.empty(width, dtype=torch.float64) for _ in range(world)]
+        dist.all_gather(parts, mine)
+        return torch.cat([parts[r][: bounds[r + 1] - bounds[r]] for r in range(world)]).numpy()
+
+    def mv(vl):
+        return al @ gather(vl)
+
+    def not_converged(rl, dl, yl):  # gmres.py:130-141 with the default max_norm
+        rn = allmax(np.max(np.abs(rl / (tol + tol * np.abs(bl)))) if rl.size else 0.0)
+        dn = allmax(np.max(np.abs(dl / (tol + tol * np.abs(yl)))) if dl.size else 0.0)
+        return rn > 1 or dn > 1
+
+    def main_gmres(yl, rl):
+        r_norm = np.sqrt(allsum(rl @ rl)[0])
+        initial_breakdown = r_norm < eps
+        basis = np.zeros((hi - lo, restart + 1))
+        basis[:, 0] = rl / (np.inf if initial_breakdown else r_norm)
+        coeff = np.eye(restart, restart + 1)
+        breakdown, k = initial_breakdown, 0
+        while k < restart and not breakdown:
+            w = mv(basis[:, k])
+            red = allsum(np.concatenate([basis.T @ w, [w @ w]]))  # fused: projections + ||w||^2
+            proj, step_norm = red[:-1], np.sqrt(red[-1])
+            w = w - basis @ proj
+            nrm = np.sqrt(allsum(w @ w)[0])
+            breakdown = bool(nrm < step_norm * eps)
+            basis[:, k + 1] = w / (np.inf if breakdown else nrm)
+            proj[k + 1] = nrm
+            coeff[k, :] = proj
+            k += 1
+        beta_vec = np.zeros(restart + 1)
+        beta_vec[0] = r_norm
+        z = qr_compute(qr_init(np.ascontiguousarray(coeff.T)), beta_vec)  # replicated small solve
+        diff = basis[:, :-1] @ z
+        return yl + diff, diff, breakdown
+
+    with np.errstate(all="ignore"):
+        yl, rl = np.zeros(hi - lo), np.zeros(hi - lo)
+        breakdown = deferred = False
+        diff = np.full(hi - lo, np.inf)
+        r_min, step, stag, ms = np.inf, 0, 0, 10 * n
+        while ((not deferred) and stag < stagnation_iters and not_converged(rl, diff, yl) and step < ms) or step == 0:
+            if step == 0:
+                y_new, diff_new, bd = yl, np.full(hi - lo, np.inf), False
+            else:
+                y_new, diff_new, bd = main_gmres(yl, rl)
+            r_new = bl - mv(y_new)
+            r_new_norm = allmax(np.max(np.abs(r_new)) if r_new.size else 0.0)
+            stag = 0 if (r_new_norm - r_min) < 0 else stag + 1
+            r_min = min(r_new_norm, r_min)
+            yl, rl, deferred, breakdown, diff = y_new, r_new, breakdown, bd, diff_new
+            step += 1
+    x = gather(yl)
+    xr, rr, st = oracle.gmres(a, b, tol, tol)
+    assert step == st["num_steps"] and rr == 0, (step, st["num_steps"], rr)
+    assert np.abs(x - xr).max() <= 1e-9 * np.abs(xr).max()
+    np.save(os.path.join(out_dir, f"gmres{rank}.npy"), x)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_row_sharded_gmres_decomposition_world2_gloo(tmp_path):
+    world = 2
+    mp.spawn(_gmres_rows_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    x0, x1 = np.load(tmp_path / "gmres0.npy"), np.load(tmp_path / "gmres1.npy")
+    assert np.array_equal(x0, x1)
