@@ -15,6 +15,7 @@
 #include <stdlib.h>
 
 #include "common.cuh"
+#include "lu_tma.cuh"
 
 namespace lxb {
 
@@ -586,6 +587,12 @@ int lu_dispatch(const T* A, int64_t sA, const T* b, int64_t sb, T* x, T* lu, int
   if (SOLVE && (b == nullptr || x == nullptr)) return LXB_E_BADARG;
   if (!SOLVE && (lu == nullptr || piv == nullptr)) return LXB_E_BADARG;
   if (batch == 0 || n == 0) return 0;
+  if constexpr (sizeof(T) == 4) {
+    // BASELINE configs[1]: TMA-staged FFMA2 kernel (lu_tma.cu); LXB_LU_LEGACY=1 keeps the cp.async one
+    static const bool legacy = getenv("LXB_LU_LEGACY") != nullptr;
+    if (!legacy && lu32_tma_eligible(A, sA, lu, batch, n))
+      return lu32_tma_launch(A, sA, b, sb, x, lu, piv, batch, SOLVE, st);
+  }
   if (n <= 8) return launch_lu_warp<T, 8, SOLVE>(A, sA, b, sb, x, lu, piv, batch, n, st);
   if (n <= 16) return launch_lu_warp<T, 16, SOLVE>(A, sA, b, sb, x, lu, piv, batch, n, st);
   if (n <= 32) return launch_lu_warp<T, 32, SOLVE>(A, sA, b, sb, x, lu, piv, batch, n, st);

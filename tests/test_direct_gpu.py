@@ -4,7 +4,8 @@ import pytest
 
 import oracle
 from oracle import gen
-from tests.helpers import assert_close, dev, host
+from tests.helpers import (assert_close, assert_close_tol, backward_error, cond_2, cond_inf, dev, host,
+                           tol_for, EPS)
 
 pytestmark = pytest.mark.gpu
 
@@ -26,9 +27,13 @@ def test_cholesky(n, dtype, nsd):
     x = _ops().cholesky_solve(f, dev(b), nsd)
     for i in range(4):
         st = oracle.cholesky_init(a[i], is_nsd=nsd)
-        assert_close(np.triu(host(f)[i]), np.triu(st[0]), dtype, factor=50 * n)
+        # easy SPD generator: cond of a few units -> flat north_star tolerance (1e-5 / 1e-12)
+        tol = tol_for(dtype, cond_inf(a[i]))
+        assert tol <= 10 * tol_for(dtype), "generator is expected to be well conditioned"
+        assert_close_tol(np.triu(host(f)[i]), np.triu(st[0]), tol, "factor")
         assert np.all(np.tril(host(f)[i], -1) == 0)
-        assert_close(host(x)[i], oracle.cholesky_compute(st, b[i]), dtype, factor=100 * n)
+        assert_close_tol(host(x)[i], oracle.cholesky_compute(st, b[i]), tol)
+        assert backward_error(a[i], host(x)[i], b[i]) <= 4 * n * EPS[np.dtype(dtype)]
 
 
 def test_cholesky_not_pd_gives_nan():
@@ -49,14 +54,20 @@ def test_qr(shape, dtype):
     for i in range(3):
         st = oracle.qr_init(a[i])
         xr = oracle.qr_compute(st, b[i])
-        assert_close(x[i], xr, dtype, factor=200 * max(m, n))
+        # Gaussian inputs are not well conditioned: the legitimate difference between two backward-stable
+        # Householder solves is bounded by the instance's own conditioning (kappa for a square system,
+        # kappa^2 for a least-squares / minimum-norm problem), nothing else is allowed on top of north_star
+        k2 = cond_2(a[i])
+        tol = tol_for(dtype, k2 if m == n else k2 * k2)
+        assert_close_tol(x[i], xr, tol)
         xl = np.linalg.lstsq(a[i].astype(np.float64), b[i].astype(np.float64), rcond=None)[0]
-        assert np.max(np.abs(x[i] - xl)) / np.abs(xl).max() < (1e-3 if dtype == np.float32 else 1e-9)
+        assert_close_tol(x[i], xl, tol, "solution vs float64 lstsq")
         (a_ref, taus_ref), _ = st
         rows, cols = a_ref.shape
-        # R and taus follow LAPACK's sign conventions (geqr2): compare directly
-        assert_close(np.triu(host(aq)[i][:cols]), np.triu(a_ref[:cols]), dtype, factor=500 * max(m, n))
-        assert_close(host(taus)[i], taus_ref, dtype, factor=500 * max(m, n))
+        # R and taus follow LAPACK's sign conventions (geqr2): compare directly, relative to max |R|
+        r_gpu, r_ref = np.triu(host(aq)[i][:cols]), np.triu(a_ref[:cols])
+        assert np.max(np.abs(r_gpu - r_ref)) <= tol_for(dtype, k2) * np.max(np.abs(r_ref))
+        assert np.max(np.abs(host(taus)[i] - taus_ref)) <= tol_for(dtype, k2)
 
 
 def test_qr_transposed_state():
@@ -77,7 +88,7 @@ def test_tridiagonal_dominant(n, dtype):
     x = host(_ops().tridiagonal_solve(dev(d), dev(l), dev(u), dev(b)))
     for i in range(0, 70, 9):
         xr = oracle.tridiagonal_compute(d[i], l[i], u[i], b[i])
-        assert_close(x[i], xr, dtype, factor=50)
+        assert_close(x[i], xr, dtype)  # diagonally dominant BASELINE generator: flat 1e-5 / 1e-12
 
 
 @pytest.mark.parametrize("dtype", [np.float32, np.float64])
@@ -92,10 +103,12 @@ def test_tridiagonal_general_needs_pivoting(n, dtype):
     x = host(_ops().tridiagonal_solve(dev(d), dev(l), dev(u), dev(b)))
     for i in range(40):
         T = np.diag(d[i]) + np.diag(l[i], -1) + np.diag(u[i], 1)
-        if np.linalg.cond(T.astype(np.float64)) > 1000:
+        kappa = cond_inf(T)
+        if kappa > 1000:
             continue
         xr = oracle.tridiagonal_compute(d[i], l[i], u[i], b[i])
-        assert_close(x[i], xr, dtype, factor=2000)
+        assert_close_tol(x[i], xr, tol_for(dtype, kappa))
+        assert backward_error(T, x[i], b[i]) <= 8 * EPS[np.dtype(dtype)] * 10  # gtsv growth factor slack
 
 
 def test_tridiagonal_c5_properties():
@@ -107,7 +120,7 @@ def test_tridiagonal_c5_properties():
     r[:, 1:] += l * x[:, :-1]
     assert np.max(np.abs(r)) < 5e-5
     xr = oracle.tridiagonal_compute(d[12345], l[12345], u[12345], b[12345])
-    assert_close(x[12345], xr, np.float32, factor=20)
+    assert_close(x[12345], xr, np.float32)
 
 
 @pytest.mark.parametrize("dtype", [np.float32, np.float64])
@@ -136,7 +149,10 @@ def test_diagonal_and_triangular(dtype):
                     x = host(_ops().triangular_solve(dev(a), dev(bb), lower, unit, trans))
                     for i in range(3):
                         xr = oracle.triangular_compute(a[i], bb[i], lower, unit, int(trans))
-                        assert_close(x[i], xr, dtype, factor=1e4)
+                        t = np.tril(a[i]) if lower else np.triu(a[i])
+                        if unit:
+                            t = t - np.diag(np.diag(t)) + np.eye(n)
+                        assert_close_tol(x[i], xr, tol_for(dtype, cond_inf(t)))
 
 
 @pytest.mark.parametrize("shape,dtype", [((4096, 256), np.float32), ((8192, 130), np.float64),
@@ -150,14 +166,19 @@ def test_qr_large_blocked(shape, dtype):
     a, b, _ = gen.tall_lstsq(m + n, m, n, dtype)
     aq, taus = _ops().qr_factor(dev(a[None]))
     x = host(_ops().qr_solve(aq, taus, dev(b[None]), False))[0]
-    (a_ref, taus_ref), _ = oracle.qr_init(a)
-    tolf = 2e-3 if dtype == np.float32 else 1e-9
+    # reference = LAPACK geqrf in FLOAT64 on the same input (identical sign conventions): with m up to
+    # 3e5 the float32 LAPACK factors themselves carry ~sqrt(m) eps of rounding, so they cannot arbitrate
+    # a 1e-5 comparison; the float64 factors can.  The C5 generator is well conditioned (kappa ~ 1-3).
+    (a_ref, taus_ref), _ = oracle.qr_init(a.astype(np.float64))
+    k2 = cond_2(a) if m * n <= 1 << 23 else (1 + np.sqrt(n / m)) / (1 - np.sqrt(n / m))
+    tol = tol_for(dtype, k2 * k2)
+    assert tol <= 3 * tol_for(dtype), "C5 generator is expected to be well conditioned"
     r_gpu, r_ref = np.triu(host(aq)[0][:n]), np.triu(a_ref[:n])
-    assert np.max(np.abs(r_gpu - r_ref)) <= tolf * np.max(np.abs(r_ref))
-    assert np.max(np.abs(host(taus)[0] - taus_ref)) <= tolf
+    assert np.max(np.abs(r_gpu - r_ref)) <= tol * np.max(np.abs(r_ref)), "R"
+    assert np.max(np.abs(host(taus)[0] - taus_ref)) <= tol, "taus"
     v_gpu, v_ref = np.tril(host(aq)[0], -1), np.tril(a_ref, -1)
-    assert np.max(np.abs(v_gpu - v_ref)) <= 10 * tolf * max(1.0, np.max(np.abs(v_ref)))
+    assert np.max(np.abs(v_gpu - v_ref)) <= tol * max(1.0, np.max(np.abs(v_ref))), "Householder vectors"
     xl = np.linalg.lstsq(a.astype(np.float64), b.astype(np.float64), rcond=None)[0]
-    assert np.max(np.abs(x - xl)) / np.abs(xl).max() < (5e-4 if dtype == np.float32 else 1e-9)
+    assert_close_tol(x, xl, tol, "solution vs float64 lstsq")
     xr = oracle.qr_compute(oracle.qr_init(a), b)
-    assert_close(x, xr, dtype, factor=2000)
+    assert_close_tol(x, xr, tol, "solution vs float32 LAPACK")

@@ -114,3 +114,35 @@ def test_singular_gives_nonfinite():
     x, _, _ = _ops().lu_factor_solve(dev(a), dev(np.ones((2, 4), np.float32)), False)
     x = host(x)
     assert not np.all(np.isfinite(x[0])) and np.allclose(x[1], 1.0)
+
+
+@pytest.mark.parametrize("scale", [1e-42, 1e-38, 1e-30, 1e30, 3e37])
+def test_extreme_pivots_take_the_ieee_division_path(scale):
+    """Denormal / huge pivots: 1/pivot leaves the fast MUFU.RCP+Newton range and must still be the
+    correctly rounded IEEE quotient the C oracle computes (rcp_slow in csrc/lu_tma.cu)."""
+    a, b, _ = gen.gaussian_systems(77, 130, 32, np.float32)
+    a = (a.astype(np.float64) * scale).astype(np.float32)
+    a[3, 5, :] = 0.0  # one singular system: inf / NaN must propagate identically
+    x_ref, lu_ref, piv_ref = clib.lu_factor_solve(a, b)
+    x, lu, piv = _ops().lu_factor_solve(dev(a), dev(b), True)
+    assert np.array_equal(host(piv), piv_ref)
+    assert np.array_equal(host(lu), lu_ref, equal_nan=True)
+    assert np.array_equal(host(x), x_ref, equal_nan=True)
+    x2, _, _ = _ops().lu_factor_solve(dev(a), dev(b), False)
+    assert np.array_equal(host(x2), x_ref, equal_nan=True)
+
+
+def test_strided_and_odd_batches_tma_path():
+    """Batch sizes around the 8-warp CTA granularity and a strided operand (systems 2 apart)."""
+    for batch in (1, 7, 8, 9, 1185, 1191):
+        a, b, _ = gen.gaussian_systems(batch, batch, 32, np.float32)
+        x_ref, lu_ref, piv_ref = clib.lu_factor_solve(a, b)
+        x, lu, piv = _ops().lu_factor_solve(dev(a), dev(b), True)
+        assert np.array_equal(host(x), x_ref) and np.array_equal(host(lu), lu_ref)
+        assert np.array_equal(host(piv), piv_ref)
+        x2, _, _ = _ops().lu_factor_solve(dev(a), dev(b), False)
+        assert np.array_equal(host(x2), x_ref)
+    a, b, _ = gen.gaussian_systems(3, 64, 32, np.float32)
+    x_ref, _, _ = clib.lu_factor_solve(a[::2], b[::2])
+    x, _, _ = _ops().lu_factor_solve(dev(a)[::2], dev(b)[::2], False)
+    assert np.array_equal(host(x), x_ref)
