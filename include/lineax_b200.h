@@ -208,6 +208,14 @@ LXB_DECL_KRYLOV(f64, double)
 LXB_DECL_VEC(f32, float)
 LXB_DECL_VEC(f64, double)
 
+/* Gram matrix of the normal equations, lineax/_solver/normal.py:111-117 (`conj(op.T) @ op` / `op @ conj(op.T)`):
+ * G[batch,n,n] = A^T A (flags = 0) or G[batch,m,m] = A A^T (LXB_TRANS) for A[batch,m,n] row-major. */
+#define LXB_DECL_GRAM(sfx, T)                                                                    \
+  int lxb_gram_##sfx(const T* A, int64_t stride_A, T* G, int64_t batch, int32_t m, int32_t n,    \
+                     int32_t flags, lxb_stream_t stream);
+LXB_DECL_GRAM(f32, float)
+LXB_DECL_GRAM(f64, double)
+
 /* ------------------------------------------------ multi-GPU, row-sharded --
  * Restarted GMRES on ONE large system partitioned by rows over the GPUs of an NVLink box
  * (one process per GPU).  Rank r owns rows [row_offset, row_offset + n_local) of A
@@ -274,6 +282,12 @@ int lxb_lu_factor_solve_f32_host(const float* A_host, const float* b_host, float
                                  int64_t batch, int32_t n, void* device_scratch,
                                  size_t scratch_bytes, lxb_stream_t stream);
 size_t lxb_host_scratch_bytes(int64_t batch, int32_t n, int32_t elem_bytes);
+
+/* fp32 FMA throughput probe: launches `iters` x 64 dependent-chain FMAs per thread on every SM
+ * (`packed` != 0: fma.rn.f32x2) and returns the flop count of the launch in *flops (host pointer).
+ * bench.py times it with CUDA events to MEASURE the FP32 roofline denominator of the factorisations
+ * (BASELINE.md section 2 asks for a measured, not nominal, peak).  `out`: >= 1 float of device memory. */
+int lxb_fp32_fma_probe(float* out, int32_t iters, int32_t packed, double* flops, lxb_stream_t stream);
 
 #ifdef __cplusplus
 }

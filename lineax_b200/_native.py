@@ -66,6 +66,7 @@ for _sfx, _T in (("f32", c_float), ("f64", c_double)):
     _decl(f"lxb_diag_mv_{_sfx}", [P, c_int64, P, c_int64, P, c_int64, c_int32, P])
     _decl(f"lxb_tridiag_mv_{_sfx}", [P, P, P, c_int64, P, c_int64, P, c_int64, c_int32, P])
     _decl(f"lxb_norms_{_sfx}", [P, c_int64, P, c_int64, P, c_int64, c_int64, P])
+    _decl(f"lxb_gram_{_sfx}", [P, c_int64, P, c_int64, c_int32, c_int32, c_int32, P])
     _decl(f"lxb_cholesky_factor_{_sfx}", [P, c_int64, P, c_int64, c_int32, c_int32, P])
     _decl(f"lxb_cholesky_solve_{_sfx}", [P, c_int64, P, c_int64, P, c_int64, c_int32, c_int32, P])
     _decl(f"lxb_qr_factor_{_sfx}", [P, c_int64, P, P, c_int64, c_int32, c_int32, P, c_size_t, P])
@@ -112,6 +113,7 @@ for _sfx, _T in (("f32", c_float), ("f64", c_double)):
     _decl(f"lxb_lsmr_rowsharded_symm_bytes_{_sfx}", [c_int32, c_int32], c_size_t)
 _decl("lxb_lu_factor_solve_f32_host", [P, P, P, c_int64, c_int32, P, c_size_t, P])
 _decl("lxb_host_scratch_bytes", [c_int64, c_int32, c_int32], c_size_t)
+_decl("lxb_fp32_fma_probe", [P, c_int32, c_int32, P, P])
 
 
 class NativeError(RuntimeError):

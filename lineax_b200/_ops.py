@@ -200,9 +200,12 @@ def _throw_if_failed(result: Tensor) -> Tensor:
     """`throw=True` (lineax/_solve.py:124-128): raise on any non-successful code (host sync)."""
     from ._solution import RESULTS, LinearSolveError
 
-    codes = result.reshape(-1).tolist()
-    bad = [c for c in codes if c != 0]
-    if bad:
+    flat = result.reshape(-1)
+    # one scalar leaves the device (the reference's error_if is asynchronous; callers that issue many
+    # small solves should pass throw=False and inspect `Solution.result` themselves)
+    if bool((flat != 0).any()):
+        codes = flat.tolist()
+        bad = [c for c in codes if c != 0]
         where = "" if len(codes) == 1 else f" ({len(bad)} of {len(codes)} systems failed)"
         raise LinearSolveError(RESULTS[bad[0]] + where)
     return result.clone()
@@ -229,6 +232,25 @@ def _matvec(a: Tensor, x: Tensor, trans: bool) -> Tensor:
 
 
 matvec = _define("matvec", _matvec, n_out=1)
+
+
+def _gram(a: Tensor, aat: bool) -> Tensor:
+    """A^T A (aat False) or A A^T (aat True): the operator of the normal equations (normal.py:111-117)."""
+    _check_cuda(a)
+    m, n = a.shape[-2], a.shape[-1]
+    full = _batch(a, 2)
+    B = math.prod(full)
+    sfx = nat.suffix(a.dtype)
+    g = m if aat else n
+    with torch.cuda.device(a.device):
+        a_ = a.contiguous()
+        out = torch.empty(full + (g, g), dtype=a.dtype, device=a.device)
+        nat.call(f"lxb_gram_{sfx}", a_.data_ptr(), m * n, out.data_ptr(), B, m, n, nat.TRANS if aat else 0,
+                 _stream())
+    return out
+
+
+gram = _define("gram", _gram, n_out=1)
 
 
 def _diag_mv(d: Tensor, x: Tensor) -> Tensor:

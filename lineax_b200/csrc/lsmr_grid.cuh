@@ -73,8 +73,8 @@ __device__ __forceinline__ void grid_reduce_cols(const GridTeam<T>& team, const 
 // Returns this CTA's sum of u'_i^2 (identical in every thread).
 template <typename T, int CH>
 __device__ __forceinline__ T lsmr_fused_pass(const T* __restrict__ A, int n, int rlo, int rhi,
-                                             const T* __restrict__ vin, const T* __restrict__ uold,
-                                             T* __restrict__ unew, T s1, T s2, T* __restrict__ pout,
+                                             const T* vin, const T* uold, T* unew /* may alias uold */,
+                                             T s1, T s2, T* __restrict__ pout,
                                              T* red) {
   constexpr int V = 16 / sizeof(T);
   constexpr int R = 4;

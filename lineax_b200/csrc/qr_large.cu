@@ -834,7 +834,7 @@ __global__ void __launch_bounds__(kTcThreads)
       for (int spin = 0; spin < (1 << 22) && !done; ++spin)
         asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}\n"
                      : "=r"(done) : "r"(tc::smem_u32(mbar)), "r"(phase) : "memory");
-      if (!done && tid == 0) atomicExch(err, 1);  // never hang the GPU: report and carry on
+      if (!done) __trap();  // bounded wait: fail LOUDLY (launch error) instead of updating with stale TMEM
       phase ^= 1;
     }
     asm volatile("tcgen05.fence::after_thread_sync;");
@@ -993,7 +993,7 @@ __global__ void __launch_bounds__(kTcThreads, 3)
     for (int spin = 0; spin < (1 << 22) && !done; ++spin)
       asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}\n"
                    : "=r"(done) : "r"(tc::smem_u32(mbar)), "r"(phase) : "memory");
-    if (!done && tid == 0) atomicExch(err, 1);
+    if (!done) __trap();  // bounded wait: fail loudly, never continue with stale TMEM
     phase ^= 1;
     asm volatile("tcgen05.fence::after_thread_sync;");
     uint32_t r[32];
@@ -1304,7 +1304,11 @@ int qr_large_factor(const T* A, T* a, T* taus, int m, int n, void* ws, size_t ws
     const int ncols = n - j0 - kPB;
     if (ncols <= 0) break;
     const int tiles = (ncols + kUpCols - 1) / kUpCols;
+#ifdef LXB_QR_WTC_EXPERIMENT  // tcgen05 W = V^T A2: compile-time opt-in until its in-situ parity run is green
     static const bool use_wtc = [] { const char* e = getenv("LXB_QR_WTC"); return e && atoi(e) == 1; }();
+#else
+    constexpr bool use_wtc = false;
+#endif
     const bool w_tc = use_wtc && sizeof(T) == 4 && (n % 4 == 0) && ((reinterpret_cast<uintptr_t>(a) & 15) == 0);
     const int wtiles = w_tc ? tiles : (ncols + kW2Tile - 1) / kW2Tile;
     // row groups: about two waves of CTAs at the kernel's occupancy, whatever the tile count is

@@ -69,8 +69,9 @@ def qr_init(A):
     transpose = n > m
     if transpose:
         A = A.T
-    (geqrf,) = _lapack(("geqrf",), A)
-    a, taus, _, info = geqrf(np.asfortranarray(A))
+    geqrf, geqrf_lwork = _lapack(("geqrf", "geqrf_lwork"), A)
+    lwork, _ = geqrf_lwork(*A.shape)  # optimal workspace: LAPACK's blocked algorithm, as jaxlib queries it
+    a, taus, _, info = geqrf(np.asfortranarray(A), lwork=int(lwork))
     assert info == 0
     return (np.ascontiguousarray(a), taus), transpose
 

@@ -37,7 +37,7 @@ def main():
         x1, r1, s1 = _ops.gmres(A[None], B[None], None, None, tol, tol, 10 * n, 20, 20, 0)
         err = np.abs(x - xr).max() / np.abs(xr).max()
         err1 = np.abs(x - x1[0].cpu().numpy()).max() / np.abs(xr).max()
-        good = int(res) == rr and abs(int(steps) - st["num_steps"]) <= 2 and err < (2e-4 if dtype == np.float32 else 1e-9)
+        good = int(res) == rr and abs(int(steps) - st["num_steps"]) <= 2 and err < (1e-5 if dtype == np.float32 else 1e-11)
         ok &= good
         if rank == 0:
             print(f"n={n} {dtype.__name__}: result {int(res)} (oracle {rr}) steps {int(steps)} (oracle {st['num_steps']}, "

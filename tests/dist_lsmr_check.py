@@ -40,7 +40,7 @@ def main():
         err = np.abs(x - xr).max() / np.abs(xr).max()
         err1 = np.abs(x - x1[0].cpu().numpy()).max() / np.abs(xr).max()
         good = (same and int(res) == rr and abs(int(steps) - st["num_steps"]) <= 2
-                and int(stats["istop"]) == st["istop"] and err < (2e-4 if dtype == np.float32 else 1e-9))
+                and int(stats["istop"]) == st["istop"] and err < (1e-5 if dtype == np.float32 else 1e-11))
         ok &= good
         if rank == 0:
             print(f"{m}x{n} {dtype.__name__}: result {int(res)} (oracle {rr}) steps {int(steps)} (oracle "

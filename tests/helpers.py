@@ -73,3 +73,11 @@ def backward_error(a, x, b):
     r = a @ x - b
     den = np.abs(a).sum(-1).max() * np.abs(x).max() + np.abs(b).max()
     return float(np.abs(r).max() / max(den, 1e-300))
+
+
+def max_cond(a):
+    """Largest 2-norm condition number over a batch of matrices (float64)."""
+    a = np.asarray(a, dtype=np.float64)
+    if a.ndim == 2:
+        return cond_2(a)
+    return max(cond_2(m) for m in a)

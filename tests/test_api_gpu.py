@@ -321,3 +321,59 @@ def test_operator_mv_and_norms():
     assert np.isclose(float(lx.max_norm(x)), np.abs(flat).max())
     assert np.isclose(float(lx.tree_dot(x, x)), flat @ flat)
     assert float(lx.two_norm(t64([-3.0]))) == 3.0
+
+
+def test_gram_kernel_matches_float64():
+    """lxb_gram_* (the operator of the normal equations, normal.py:111-117)."""
+    from lineax_b200 import _ops
+
+    rng = np.random.default_rng(0)
+    for (m, n), dt in (((5, 3), np.float64), ((3, 5), np.float64), ((130, 70), np.float32), ((64, 200), np.float32)):
+        a = rng.standard_normal((2, m, n)).astype(dt)
+        A = torch.as_tensor(a).cuda()
+        g1 = _ops.gram(A, False).cpu().numpy()
+        g2 = _ops.gram(A, True).cpu().numpy()
+        a64 = a.astype(np.float64)
+        tol = 1e-12 if dt == np.float64 else 1e-5
+        assert np.max(np.abs(g1 - np.einsum("bki,bkj->bij", a64, a64))) <= tol * np.max(np.abs(g1))
+        assert np.max(np.abs(g2 - np.einsum("bik,bjk->bij", a64, a64))) <= tol * np.max(np.abs(g2))
+        assert np.array_equal(g1, np.swapaxes(g1, -1, -2)), "exactly symmetric"
+
+
+@pytest.mark.parametrize("shape", [(12, 7), (7, 12)])
+def test_normal_cg_preconditioner_and_y0(shape):
+    """lineax/_solver/normal.py:31-52: an outer preconditioner M ~ pinv(A) reaches the inner CG as
+    M M^* (tall) / M^* M (wide), tagged positive semidefinite; y0 is mapped to M^* y0 in the wide case.
+    With the exact pseudo-inverse the preconditioned normal equations converge in a handful of steps,
+    and the solution must be the least-squares / minimum-norm one."""
+    import oracle
+
+    lx = _lx()
+    m, n = shape
+    rng = np.random.default_rng(m * 31 + n)
+    a = rng.standard_normal((m, n))
+    b = rng.standard_normal(m)
+    pinv = np.linalg.pinv(a)
+    x_ref = np.linalg.lstsq(a, b, rcond=None)[0]
+    op = lx.MatrixLinearOperator(t64(a))
+    solver = lx.Normal(lx.CG(rtol=1e-10, atol=1e-10))
+    plain = lx.linear_solve(op, t64(b), solver)
+    pre = lx.linear_solve(op, t64(b), solver, options={"preconditioner": lx.MatrixLinearOperator(t64(pinv))})
+    assert np.allclose(plain.value.cpu().numpy(), x_ref, rtol=1e-7, atol=1e-9)
+    assert np.allclose(pre.value.cpu().numpy(), x_ref, rtol=1e-7, atol=1e-9)
+    assert int(pre.stats["num_steps"]) <= 4 <= int(plain.stats["num_steps"]) + 4
+    # oracle parity of the inner solve: CG on the Gram matrix with the squared preconditioner
+    tall = m >= n
+    gram = a.T @ a if tall else a @ a.T
+    msq = pinv @ pinv.T if tall else pinv.T @ pinv
+    rhs = a.T @ b if tall else b
+    yr, rr, st = oracle.cg(gram, rhs, 1e-10, 1e-10, preconditioner=msq)
+    xr = yr if tall else a.T @ yr
+    assert int(pre.result) == rr == 0 and abs(int(pre.stats["num_steps"]) - st["num_steps"]) <= 2
+    assert np.allclose(pre.value.cpu().numpy(), xr, rtol=1e-8, atol=1e-10)
+    # y0: the exact solution as initial guess stops immediately (tall: y0 is passed through)
+    if tall:
+        warm = lx.linear_solve(op, t64(b), solver, options={"y0": t64(x_ref)})
+        assert int(warm.stats["num_steps"]) <= 1
+    assert solver.assume_full_rank() is True
+    assert lx.Normal(lx.Cholesky()).assume_full_rank() == lx.Cholesky().assume_full_rank()

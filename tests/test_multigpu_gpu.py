@@ -1,4 +1,6 @@
-"""Multi-GPU row-sharded GMRES and LSMR (need >= 2 CUDA devices; skipped otherwise): launch
+"""Row-sharded GMRES and LSMR.  The fused peer-memory kernels are exercised on EVERY box: as a 1-rank group
+(symmetric-memory rendezvous with itself; every exchange round, flag and fold of the kernels still runs) and,
+where >= 2 CUDA devices exist, across 2 GPUs.  Launch
 tests/dist_gmres_check.py / tests/dist_lsmr_check.py under torchrun, which check the fused
 peer-memory kernels against the oracle and the single-GPU kernels."""
 import os
@@ -26,3 +28,21 @@ def test_row_sharded_lsmr_two_gpus():
            "--master-addr", "127.0.0.1", "--master-port", "29534", os.path.join(ROOT, "tests", "dist_lsmr_check.py")]
     out = subprocess.run(cmd, capture_output=True, text=True, timeout=300, cwd=ROOT)
     assert "DIST_LSMR_ALL_OK" in out.stdout, out.stdout[-2000:] + out.stderr[-2000:]
+
+
+def _run(script, nproc, port, token):
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(nproc),
+           "--master-addr", "127.0.0.1", "--master-port", str(port), os.path.join(ROOT, "tests", script)]
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=ROOT)
+    assert token in out.stdout, out.stdout[-3000:] + out.stderr[-3000:]
+    return out.stdout
+
+
+def test_row_sharded_gmres_one_rank_group():
+    """gmres_dist_kernel on a 1-rank group (runs on the driver's single-GPU box)."""
+    _run("dist_gmres_check.py", 1, 29535, "DIST_GMRES_ALL_OK")
+
+
+def test_row_sharded_lsmr_one_rank_group():
+    """lsmr_dist_kernel on a 1-rank group (runs on the driver's single-GPU box)."""
+    _run("dist_lsmr_check.py", 1, 29536, "DIST_LSMR_ALL_OK")
