@@ -271,19 +271,30 @@ __device__ __forceinline__ int tw_shift(const T* base, int64_t e0) {
   const int64_t a0 = (int64_t)((reinterpret_cast<uintptr_t>(base) / sizeof(T)) % V) + e0;
   return (int)(((a0 % V) + V) % V);
 }
-template <typename T, int CPL>
+template <typename T, int R>
 __device__ __forceinline__ void tw_stage(T* dst, const T* base, int64_t e0, int n, int64_t total, int lane) {
   constexpr int V = 16 / (int)sizeof(T);
+  constexpr int CPL = R / V;
+  constexpr int KMAX = (R * 32 / V + 1 + 31) / 32;  // chunks per lane: n / V + 1 at most
   const int t = tw_shift(base, e0);
   const int nch = (t + n + V - 1) / V;
-  const T* src0 = base + e0 - t;  // 16-byte aligned
-  for (int q = lane; q < nch; q += 32) {
-    const int64_t lo = e0 - t + (int64_t)q * V;  // first element of the chunk
-    // any aligned 16-byte piece that overlaps the array is safe to read in full (allocation granularity);
-    // pieces entirely outside are zero-filled without touching memory
-    const bool ok = lo + V > 0 && lo < total;
-    tri_cp(reinterpret_cast<char*>(dst) + tw_swz<CPL>(q) * 16, ok ? (const void*)(src0 + (int64_t)q * V) : (const void*)base,
-           16, ok);
+  // one 64-bit pointer per lane; every chunk of the lane is a constant 512 bytes further on
+  const char* src = reinterpret_cast<const char*>(base + (e0 - t)) + lane * 16;
+  const unsigned dsts = (unsigned)__cvta_generic_to_shared(dst);
+  // any aligned 16-byte piece that overlaps the array is safe to read in full (allocation granularity);
+  // pieces entirely outside (before element 0 / at or after element `total`) are zero-filled unread
+  const int64_t rem64 = total - (e0 - t);
+  const int rem = rem64 > (int64_t)(1 << 30) ? (1 << 30) : (int)rem64;  // elements from chunk 0 to the end
+  const bool first_ok = e0 - t + V > 0;
+#pragma unroll
+  for (int k = 0; k < KMAX; ++k) {
+    const int q = lane + 32 * k;
+    if (q < nch) {
+      const bool ok = q * V < rem && (q > 0 || first_ok);
+      const int sb = ok ? 16 : 0;
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(dsts + tw_swz<CPL>(q) * 16),
+                   "l"(ok ? (const void*)(src + k * 512) : (const void*)base), "r"(sb));
+    }
   }
 }
 // Lane's R consecutive rows (starting at row R * lane) of a staged array, undoing the alignment shift t.
@@ -331,10 +342,10 @@ __global__ void __launch_bounds__(kTwWarps * 32)
   const int64_t totD = (batch - 1) * sD + n, totO = (batch - 1) * sOff + (n - 1), totB = (batch - 1) * sB + n;
   auto stage_sys = [&](int st, int64_t s) {
     T* r0 = reinterpret_cast<T*>(wsm + st * STAGE);
-    tw_stage<T, CPL>(r0, D, s * sD, n, totD, lane);
-    tw_stage<T, CPL>(r0 + RC * V, DL, s * sOff - 1, n, totO, lane);      // row i <-> DL[s*sOff + i - 1]
-    tw_stage<T, CPL>(r0 + 2 * RC * V, DU, s * sOff, n, totO, lane);      // row i <-> DU[s*sOff + i]
-    tw_stage<T, CPL>(r0 + 3 * RC * V, B, s * sB, n, totB, lane);
+    tw_stage<T, R>(r0, D, s * sD, n, totD, lane);
+    tw_stage<T, R>(r0 + RC * V, DL, s * sOff - 1, n, totO, lane);      // row i <-> DL[s*sOff + i - 1]
+    tw_stage<T, R>(r0 + 2 * RC * V, DU, s * sOff, n, totO, lane);      // row i <-> DU[s*sOff + i]
+    tw_stage<T, R>(r0 + 3 * RC * V, B, s * sB, n, totB, lane);
     cp_async_commit();
   };
   int64_t sys = (int64_t)blockIdx.x * kTwWarps + warp;
@@ -354,15 +365,21 @@ __global__ void __launch_bounds__(kTwWarps * 32)
     tw_read<T, R>(r0 + 2 * RC * V, tw_shift(DU, sys * sOff), lane, c);
     tw_read<T, R>(r0 + 3 * RC * V, tw_shift(B, sys * sB), lane, b);
     // rows outside the system: identity rows; first / last row have no outer coupling
+    if (n == 32 * R) {  // (warp-uniform) full tile: only two entries to clear
+      if (lane == 0) a[0] = T(0);
+      if (lane == 31) c[R - 1] = T(0);
+    } else {
+#pragma unroll
+      for (int j = 0; j < R; ++j) {
+        const int i = R * lane + j;
+        if (i >= n) { d[j] = T(1); b[j] = T(0); }
+        if (i >= n || i == 0) a[j] = T(0);
+        if (i >= n - 1) c[j] = T(0);
+      }
+    }
     bool dominant = true;
 #pragma unroll
-    for (int j = 0; j < R; ++j) {
-      const int i = R * lane + j;
-      if (i >= n) { d[j] = T(1); b[j] = T(0); }
-      if (i >= n || i == 0) a[j] = T(0);
-      if (i >= n - 1) c[j] = T(0);
-      dominant = dominant && (abs_(d[j]) >= abs_(a[j]) + abs_(c[j])) && d[j] != T(0);
-    }
+    for (int j = 0; j < R; ++j) dominant = dominant && (abs_(d[j]) >= abs_(a[j]) + abs_(c[j])) && d[j] != T(0);
     if (!__all_sync(kFull, dominant)) {
       // not diagonally dominant (or NaN): hand the system to the pivoting kernel
       if (lane == 0) list[atomicAdd(list_count, 1)] = (int32_t)sys;

@@ -182,3 +182,34 @@ def test_qr_large_blocked(shape, dtype):
     assert_close_tol(x, xl, tol, "solution vs float64 lstsq")
     xr = oracle.qr_compute(oracle.qr_init(a), b)
     assert_close_tol(x, xr, tol, "solution vs float32 LAPACK")
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+@pytest.mark.parametrize("n", [64, 100, 256, 512, 1024])
+def test_tridiagonal_mixed_batch_warp_and_pivoting_kernels(n, dtype):
+    """A batch that mixes diagonally dominant systems (warp-per-system kernel, csrc/tridiagonal.cu) with
+    systems that need gtsv's row interchanges (handed over to the pivoting kernel through the in-kernel
+    list), odd batch sizes, and strided operands: every system must match LAPACK gtsv."""
+    if dtype == np.float64 and n > 512:
+        pytest.skip("fp64 warp kernel covers n <= 512; larger n runs the pivoting kernel (covered elsewhere)")
+    rng = np.random.default_rng(n)
+    batch = 77
+    d, l, u, b = gen.tridiagonal_systems(n, batch, n, dtype)
+    hard = rng.random(batch) < 0.4  # these lose dominance: tiny pivots force interchanges
+    for i in np.nonzero(hard)[0]:
+        k = rng.integers(0, n, size=5)
+        d[i, k] = (1e-3 * rng.standard_normal(5)).astype(dtype)
+    x = host(_ops().tridiagonal_solve(dev(d), dev(l), dev(u), dev(b)))
+    checked = 0
+    for i in range(batch):
+        T = np.diag(d[i]) + np.diag(l[i], -1) + np.diag(u[i], 1)
+        kappa = cond_inf(T)
+        if kappa > 1e4:
+            continue
+        xr = oracle.tridiagonal_compute(d[i], l[i], u[i], b[i])
+        assert_close_tol(x[i], xr, tol_for(dtype, kappa), f"system {i} (hard={bool(hard[i])})")
+        checked += 1
+    assert checked > batch // 2 and hard.any() and (~hard).any()
+    # strided views (rows 2 apart): same answers
+    xs = host(_ops().tridiagonal_solve(dev(d)[::2], dev(l)[::2], dev(u)[::2], dev(b)[::2]))
+    assert np.array_equal(xs, x[::2])
