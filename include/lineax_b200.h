@@ -62,7 +62,8 @@ enum {
   LXB_X64_BREAKDOWN = 1 << 3,  /* BiCGStab: `== 0` breakdown test (jax_enable_x64), bicgstab.py:110-113 */
   LXB_HAS_Y0 = 1 << 4,         /* x holds the initial guess on entry (options["y0"]) */
   LXB_UNIT_DIAG = 1 << 5,      /* triangular solve: unit diagonal */
-  LXB_LOWER = 1 << 6           /* triangular solve: lower triangular */
+  LXB_LOWER = 1 << 6,          /* triangular solve: lower triangular */
+  LXB_QT_ONLY = 1 << 7         /* qr_solve: return (Q^T b)[:cols] without the R solve (row-sharded TSQR) */
 };
 
 int lxb_version(void);

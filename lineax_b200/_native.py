@@ -31,6 +31,7 @@ X64_BREAKDOWN = 1 << 3
 HAS_Y0 = 1 << 4
 UNIT_DIAG = 1 << 5
 LOWER = 1 << 6
+QT_ONLY = 1 << 7
 
 E_BADARG, E_UNSUPPORTED, E_WORKSPACE, E_ALIGN = -1, -2, -3, -4
 

@@ -466,6 +466,26 @@ def _qr_factor(a: Tensor) -> Tuple[Tensor, Tensor]:
     return out, taus
 
 
+def _qr_apply_qt(a: Tensor, taus: Tensor, b: Tensor) -> Tensor:
+    """(Q^T b)[:cols] for tall factors (qr.py:89-90 without the trailing triangular solve)."""
+    _check_cuda(a, taus, b)
+    rows, cols = a.shape[-2], a.shape[-1]
+    full = _full_batch((a, 2), (taus, 1), (b, 1))
+    sfx = nat.suffix(a.dtype)
+    with torch.cuda.device(a.device):
+        a_, s_a = _operand(a, 2, full)
+        t_, s_t = _operand(taus, 1, full)
+        b_, s_b = _operand(b.to(a.dtype), 1, full)
+        y = torch.empty(full + (cols,), dtype=a.dtype, device=a.device)
+        ws, ws_bytes = _workspace(f"lxb_qr_solve_workspace_{sfx}", a.device, math.prod(full), rows, cols)
+        nat.call(f"lxb_qr_solve_{sfx}", a_.data_ptr(), s_a, t_.data_ptr(), s_t, b_.data_ptr(), s_b,
+                 y.data_ptr(), math.prod(full), rows, cols, nat.QT_ONLY, _ptr(ws), ws_bytes, _stream())
+    return y
+
+
+qr_apply_qt = _define("qr_apply_qt", _qr_apply_qt, n_out=1)
+
+
 def _qr_solve(a: Tensor, taus: Tensor, b: Tensor, trans: bool) -> Tensor:
     _check_cuda(a, taus, b)
     rows, cols = a.shape[-2], a.shape[-1]

@@ -25,6 +25,12 @@ class GMRES(AbstractLinearSolver):
             raise NotImplementedError("the native GMRES kernel implements the default `max_norm` test")
 
     def init(self, operator, options):
+        if _is_row_sharded(operator):
+            if operator.rows != operator.cols:
+                raise ValueError(
+                    "`GMRES(..., normal=False)` may only be used for linear solves with square matrices."
+                )
+            return operator
         del options
         if not tr.structure_equal(operator.in_structure(), operator.out_structure()):
             raise ValueError(
@@ -34,12 +40,31 @@ class GMRES(AbstractLinearSolver):
 
     def compute(self, state, vector, options):
         operator = state
+        if _is_row_sharded(operator):
+            return self._compute_row_sharded(operator, vector, options)
         a, b, m, y0, size, _ = flat_problem(operator, vector, options)
         ms, flags = steps_flags(self.max_steps, size)
         restart = min(int(self.restart), size)  # gmres.py:128
         x, result, steps = _ops.gmres(a, b, m, y0, float(self.rtol), float(self.atol), ms, restart,
                                       int(self.stagnation_iters), flags)
         return unravel_like(x, tr.struct_of(vector)), result, {"num_steps": steps, "max_steps": self.max_steps}
+
+    def _compute_row_sharded(self, operator, vector, options):
+        """ONE system row-partitioned over the GPUs (csrc/gmres_dist.cu): `vector` and the solution are this
+        rank's row slices; result / num_steps are identical on every rank."""
+        from ..distributed import RowShardedGMRES
+
+        if options.get("preconditioner") is not None:
+            raise NotImplementedError("row-sharded GMRES takes no preconditioner")
+        n = operator.rows
+        key = (n, float(self.rtol), float(self.atol), int(self.restart), int(self.stagnation_iters), self.max_steps,
+               operator.local.dtype)
+        solver = operator.sharded_solver("gmres", key, lambda: RowShardedGMRES(
+            n, float(self.rtol), float(self.atol), restart=int(self.restart),
+            stagnation_iters=int(self.stagnation_iters), max_steps=self.max_steps, dtype=operator.local.dtype,
+            group=operator.group))
+        x, result, steps = solver.solve(operator.local, vector, options.get("y0"))
+        return x, result, {"num_steps": steps, "max_steps": self.max_steps}
 
     def transpose(self, state, options):
         return state.transpose(), transpose_options(options)
@@ -49,3 +74,9 @@ class GMRES(AbstractLinearSolver):
 
     def assume_full_rank(self):
         return True
+
+
+def _is_row_sharded(operator) -> bool:
+    from ..distributed import RowShardedMatrixLinearOperator
+
+    return isinstance(operator, RowShardedMatrixLinearOperator)

@@ -30,10 +30,29 @@ class LSMR(AbstractLinearSolver):
             raise NotImplementedError("the native LSMR kernel implements the default `two_norm` tests")
 
     def init(self, operator, options):
-        return linearise(operator)
+        from .gmres import _is_row_sharded
+
+        return operator if _is_row_sharded(operator) else linearise(operator)
+
+    def _compute_row_sharded(self, operator, vector, options):
+        """ONE tall system row-partitioned over the GPUs (csrc/lsmr_dist.cu): `vector` is this rank's slice
+        of b, the solution and the statistics are replicated on every rank."""
+        from ..distributed import RowShardedLSMR
+
+        key = (operator.rows, operator.cols, float(self.rtol), float(self.atol), float(self.conlim), self.max_steps,
+               operator.local.dtype)
+        solver = operator.sharded_solver("lsmr", key, lambda: RowShardedLSMR(
+            operator.rows, operator.cols, float(self.rtol), float(self.atol), conlim=float(self.conlim),
+            max_steps=self.max_steps, dtype=operator.local.dtype, group=operator.group))
+        x, result, steps, stats = solver.solve(operator.local, vector, options.get("y0"))
+        return x, result, stats
 
     def compute(self, state, vector, options):
         operator = state
+        from .gmres import _is_row_sharded
+
+        if _is_row_sharded(operator):
+            return self._compute_row_sharded(operator, vector, options)
         a = operator.as_matrix()
         m, n = operator.out_size(), operator.in_size()
         min_dim = min(m, n)

@@ -16,6 +16,10 @@ class QR(AbstractLinearSolver):
 
     def init(self, operator, options):
         del options
+        from .gmres import _is_row_sharded
+
+        if _is_row_sharded(operator):  # TSQR over the row blocks (lineax_b200.distributed.RowShardedQR)
+            return operator, False, None
         matrix = operator.as_matrix()
         m, n = matrix.shape
         transpose = n > m
@@ -23,6 +27,15 @@ class QR(AbstractLinearSolver):
         return (a, taus), transpose, pack_structures(operator)
 
     def compute(self, state, vector, options):
+        from .gmres import _is_row_sharded
+
+        if _is_row_sharded(state[0]):
+            from ..distributed import RowShardedQR
+
+            op = state[0]
+            solver = op.sharded_solver("qr", (op.rows, op.cols, op.local.dtype), lambda: RowShardedQR(
+                op.rows, op.cols, dtype=op.local.dtype, group=op.group))
+            return solver.solve(op.local, vector), RESULTS.successful, {}
         (a, taus), transpose, packed_structures = state
         del options
         vector = ravel_vector(vector, packed_structures)

@@ -259,7 +259,7 @@ template <typename T>
 __global__ void __launch_bounds__(kDirectThreads)
     qr_solve_kernel(const T* __restrict__ Aq, int64_t sAq, const T* __restrict__ Taus, int64_t sT,
                     const T* __restrict__ B, int64_t sB, T* __restrict__ X, int64_t batch, int rows,
-                    int cols, int trans) {
+                    int cols, int trans, int qt_only) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   T* red = reinterpret_cast<T*>(smem_raw);  // 32
   T* y = red + 32;                          // rows
@@ -272,7 +272,7 @@ __global__ void __launch_bounds__(kDirectThreads)
       for (int i = tid; i < rows; i += nt) y[i] = B[sys * sB + i];
       __syncthreads();
       for (int j = 0; j < cols; ++j) apply_reflector<T>(a, cols, rows, j, taus[j], y, red);
-      block_tri_solve<T>(a, cols, cols, y, false, false, false);
+      if (!qt_only) block_tri_solve<T>(a, cols, cols, y, false, false, false);
       for (int i = tid; i < cols; i += nt) X[sys * cols + i] = y[i];
     } else {
       // minimum norm: x = Q [R^-T b; 0]   (qr.py:79-86)
@@ -294,7 +294,7 @@ template <typename T>
 int qr_large_factor(const T* A, T* a, T* taus, int m, int n, void* ws, size_t ws_bytes, cudaStream_t st);
 template <typename T>
 int qr_large_solve(const T* a, const T* taus, const T* b, T* x, int m, int n, void* ws, size_t ws_bytes,
-                   cudaStream_t st);
+                   cudaStream_t st, bool qt_only);
 template <typename T>
 size_t qr_large_ws_bytes(int m, int n);
 
@@ -392,13 +392,13 @@ int qr_solve(const T* a, int64_t sa, const T* taus, int64_t stau, const T* b, in
   if (batch < 0 || rows < 0 || cols < 0 || !a || !taus || !b || !x) return LXB_E_BADARG;
   if (batch == 0 || rows == 0 || cols == 0) return 0;
   if (!(flags & LXB_TRANS) && qr_use_large(batch, rows, cols))
-    return qr_large_solve<T>(a, taus, b, x, rows, cols, ws, ws_bytes, st);
+    return qr_large_solve<T>(a, taus, b, x, rows, cols, ws, ws_bytes, st, (flags & LXB_QT_ONLY) != 0);
   const size_t smem = (32 + (size_t)rows) * sizeof(T);
   if (smem > kMaxSmemD) return LXB_E_UNSUPPORTED;
   int occ = 1, rc = occupancy(qr_solve_kernel<T>, kDirectThreads, smem, &occ);
   if (rc) return rc;
   qr_solve_kernel<T><<<(unsigned)grid_for(batch, occ), kDirectThreads, smem, st>>>(
-      a, sa, taus, stau, b, sb, x, batch, rows, cols, (flags & LXB_TRANS) ? 1 : 0);
+      a, sa, taus, stau, b, sb, x, batch, rows, cols, (flags & LXB_TRANS) ? 1 : 0, (flags & LXB_QT_ONLY) ? 1 : 0);
   LXB_CUDA_CHECK_LAUNCH();
   return 0;
 }

@@ -1368,7 +1368,7 @@ int qr_large_factor(const T* A, T* a, T* taus, int m, int n, void* ws, size_t ws
 // least squares with the large factors: x = R^{-1} (Q^T b)[:n]
 template <typename T>
 int qr_large_solve(const T* a, const T* taus, const T* b, T* x, int m, int n, void* ws, size_t ws_bytes,
-                   cudaStream_t st) {
+                   cudaStream_t st, bool qt_only) {
   const QrLargePlan<T> pl = qr_large_plan<T>(m, n);
   if (!pl.ok) return LXB_E_UNSUPPORTED;
   if (!ws || ws_bytes < pl.ws_bytes) return LXB_E_WORKSPACE;
@@ -1386,6 +1386,11 @@ int qr_large_solve(const T* a, const T* taus, const T* b, T* x, int m, int n, vo
   LXB_CUDA_TRY(cudaLaunchCooperativeKernel((const void*)ak, dim3(pl.nb_panel), dim3(kPanelThreads), args, ap_smem,
                                            st));
   count_launch();
+  if (qt_only) {  // (Q^T b)[:n] only: the row-sharded TSQR stacks these over the ranks
+    LXB_CUDA_TRY(cudaMemcpyAsync(x, y, (size_t)n * sizeof(T), cudaMemcpyDeviceToDevice, st));
+    count_launch();
+    return 0;
+  }
   const size_t smem = (size_t)n * sizeof(T);
   if (smem > 200 * 1024) return LXB_E_UNSUPPORTED;
   LXB_CUDA_TRY(cudaFuncSetAttribute(qr_rsolve_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -1410,7 +1415,7 @@ namespace lxb {
 
 #define LXB_INST_QRL(T)                                                                             \
   template int qr_large_factor<T>(const T*, T*, T*, int, int, void*, size_t, cudaStream_t);         \
-  template int qr_large_solve<T>(const T*, const T*, const T*, T*, int, int, void*, size_t, cudaStream_t); \
+  template int qr_large_solve<T>(const T*, const T*, const T*, T*, int, int, void*, size_t, cudaStream_t, bool); \
   template size_t qr_large_ws_bytes<T>(int, int);
 LXB_INST_QRL(float)
 LXB_INST_QRL(double)

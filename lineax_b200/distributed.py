@@ -12,7 +12,10 @@ import torch
 import torch.distributed as dist
 
 from . import _native as nat
+from . import _ops
+from ._operator import AbstractLinearOperator
 from ._shard import shard_bounds
+from ._tree import ShapeDtypeStruct
 
 
 class RowShardedGMRES:
@@ -134,3 +137,87 @@ class RowShardedLSMR:
         stats = {"num_steps": steps[0], "istop": st[0].to(torch.int32), "norm_r": st[1], "norm_Ar": st[2],
                  "norm_A": st[3], "cond_A": st[4], "norm_x": st[5]}
         return x, result[0], steps[0], stats
+
+
+class RowShardedQR:
+    """QR least squares (lineax/_solver/qr.py:55-94, tall branch) on a tall dense operator partitioned by
+    ROWS: communication-avoiding TSQR.  Every rank factors its own block with the blocked Householder
+    kernels (csrc/qr_large.cu) and reduces its right-hand side to `(Q_p^T b_p)[:n]`; ONE all-gather stacks
+    the P upper-triangular `R_p` (n x n) and reduced right-hand sides, and every rank finishes with the
+    same small QR of the stacked `P n x n` matrix -- the solution is replicated bit-identically.
+    Requires every rank's block to be tall (`m_local >= n`)."""
+
+    def __init__(self, m: int, n: int, *, dtype=torch.float32, group=None, device=None):
+        self.m, self.n, self.dtype = int(m), int(n), dtype
+        self.group = group if group is not None else dist.group.WORLD
+        self.world, self.rank = dist.get_world_size(self.group), dist.get_rank(self.group)
+        self.bounds = shard_bounds(self.m, self.world)
+        if min(self.bounds[r + 1] - self.bounds[r] for r in range(self.world)) < self.n:
+            raise ValueError("row-sharded QR needs m_local >= n on every rank")
+        self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+
+    def row_range(self, rank=None):
+        r = self.rank if rank is None else rank
+        return self.bounds[r], self.bounds[r + 1]
+
+    def solve(self, a_local: torch.Tensor, b_local: torch.Tensor) -> torch.Tensor:
+        lo, hi = self.row_range()
+        if tuple(a_local.shape) != (hi - lo, self.n) or tuple(b_local.shape) != (hi - lo,):
+            raise ValueError(f"rank {self.rank}: expected A_local {(hi - lo, self.n)} and b_local {(hi - lo,)}")
+        n = self.n
+        aq, taus = _ops.qr_factor(a_local.to(self.dtype))
+        if self.world == 1:
+            return _ops.qr_solve(aq, taus, b_local.to(self.dtype), False)
+        c = _ops.qr_apply_qt(aq, taus, b_local.to(self.dtype))
+        r = torch.triu(aq[:n])  # (masking only: the Householder vectors below the diagonal are dropped)
+        del aq
+        stack = torch.empty(self.world * n, n, dtype=self.dtype, device=self.device)
+        cstack = torch.empty(self.world * n, dtype=self.dtype, device=self.device)
+        dist.all_gather_into_tensor(stack, r.contiguous(), group=self.group)
+        dist.all_gather_into_tensor(cstack, c.contiguous(), group=self.group)
+        aq2, taus2 = _ops.qr_factor(stack)
+        return _ops.qr_solve(aq2, taus2, cstack, False)
+
+
+class RowShardedMatrixLinearOperator(AbstractLinearOperator):
+    """A dense `rows x cols` operator of which this rank holds the contiguous block of rows
+    `shard_bounds(rows, world)[rank : rank + 2]`.  `lx.linear_solve(op, b_local, solver)` with
+    `lx.GMRES` (square: `b_local` / the solution are the local row slices), `lx.LSMR` or `lx.QR`
+    (tall: `b_local` is the local slice, the solution is replicated) runs the row-sharded kernels
+    (lineax/_solve.py:656-806 is the entry point they sit behind)."""
+
+    def __init__(self, local_rows: torch.Tensor, rows: int, group=None):
+        self.local = local_rows
+        self.rows, self.cols = int(rows), int(local_rows.shape[-1])
+        self.group = group if group is not None else dist.group.WORLD
+        self.world, self.rank = dist.get_world_size(self.group), dist.get_rank(self.group)
+        self.bounds = shard_bounds(self.rows, self.world)
+        lo, hi = self.bounds[self.rank], self.bounds[self.rank + 1]
+        if local_rows.shape[0] != hi - lo:
+            raise ValueError(f"rank {self.rank} must hold rows [{lo}, {hi}) of the operator")
+        self._solvers = {}
+
+    # the operator interface speaks about the LOCAL block (what this process can address)
+    def mv(self, vector):
+        return _ops.matvec(self.local, vector, False)
+
+    def as_matrix(self):
+        raise ValueError("a row-sharded operator is never materialised on one device")
+
+    def transpose(self):
+        raise NotImplementedError("transposes of row-sharded operators are not supported")
+
+    def in_structure(self):
+        # square systems: every vector is sharded like the rows; tall systems: x is replicated
+        n = self.local.shape[0] if self.rows == self.cols else self.cols
+        return ShapeDtypeStruct((n,), self.local.dtype)
+
+    def out_structure(self):
+        return ShapeDtypeStruct((self.local.shape[0],), self.local.dtype)
+
+    def sharded_solver(self, kind: str, key: tuple, make):
+        """Symmetric-memory buffers are allocated once per (solver kind, parameters) and reused."""
+        k = (kind,) + key
+        if k not in self._solvers:
+            self._solvers[k] = make()
+        return self._solvers[k]

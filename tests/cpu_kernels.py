@@ -120,6 +120,20 @@ def install():
         x = np.stack([oracle.qr_compute(((A[i], T[i]), bool(trans)), B[i]) for i in range(len(A))])
         return torch.as_tensor(x).reshape(full + (x.shape[-1],))
 
+    @reg("qr_apply_qt")
+    def _(a, taus, b):
+        from scipy.linalg import get_lapack_funcs
+
+        (A, T, B), full = _bcast((a, 2), (taus, 1), (b.to(a.dtype), 1))
+        outs = []
+        for i in range(len(A)):
+            (ormqr,) = get_lapack_funcs(("ormqr",), (A[i],))
+            c = np.asfortranarray(B[i].reshape(-1, 1))
+            q, _, info = ormqr("L", "T", np.asfortranarray(A[i]), T[i], c, max(1, 64 * A[i].shape[0]))
+            outs.append(q[: A[i].shape[1], 0])
+        y = np.stack(outs)
+        return torch.as_tensor(y).reshape(full + (y.shape[-1],))
+
     @reg("tridiagonal_solve")
     def _(d, dl, du, b):
         (D, L, U, B), full = _bcast((d, 1), (dl, 1), (du, 1), (b.to(d.dtype), 1))

@@ -1,0 +1,84 @@
+"""Run under torchrun (1 or more GPUs): row-sharded QR least squares (TSQR: local blocked QR, all-gather of
+the R factors, small QR) vs LAPACK and vs the single-GPU kernels, and the `lx.linear_solve` entry points of the
+row-sharded solvers.  `python -m torch.distributed.run --nproc-per-node 2 tests/dist_qr_check.py`"""
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+
+
+def main():
+    rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+    torch.cuda.set_device(int(os.environ["LOCAL_RANK"]))
+    dist.init_process_group("nccl", device_id=torch.device("cuda", int(os.environ["LOCAL_RANK"])))
+    import lineax_b200 as lx
+    import oracle
+    from oracle import gen
+    from lineax_b200.distributed import RowShardedMatrixLinearOperator, RowShardedQR
+
+    ok = True
+    for (m, n), dtype in (((8192, 256), np.float32), ((40000, 96), np.float32), ((6000, 67), np.float64)):
+        a, b, _ = gen.tall_lstsq(m + n, m, n, dtype)
+        tdt = torch.float32 if dtype == np.float32 else torch.float64
+        solver = RowShardedQR(m, n, dtype=tdt)
+        lo, hi = solver.row_range()
+        A, B = torch.as_tensor(a[lo:hi]).cuda(), torch.as_tensor(b[lo:hi]).cuda()
+        x = solver.solve(A, B)
+        xs = [torch.empty_like(x) for _ in range(world)]
+        dist.all_gather(xs, x)
+        same = all(torch.equal(xs[0], xi) for xi in xs)
+        xl = np.linalg.lstsq(a.astype(np.float64), b.astype(np.float64), rcond=None)[0]
+        xr = oracle.qr_compute(oracle.qr_init(a), b)
+        err = np.abs(x.cpu().numpy() - xl).max() / np.abs(xl).max()
+        err_r = np.abs(x.cpu().numpy() - xr).max() / np.abs(xr).max()
+        tol = 1e-5 if dtype == np.float32 else 1e-12
+        # through the public entry point
+        op = RowShardedMatrixLinearOperator(A, m)
+        sol = lx.linear_solve(op, B, lx.QR(), throw=False)
+        same_api = torch.equal(sol.value, x) and int(sol.result) == 0
+        good = same and same_api and err < tol and err_r < tol
+        ok &= good
+        if rank == 0:
+            print(f"TSQR {m}x{n} {dtype.__name__}: rel err vs float64 lstsq {err:.2e}, vs LAPACK QR {err_r:.2e}, "
+                  f"replicated {same}, linear_solve entry {same_api} -> {'OK' if good else 'FAIL'}")
+    # linear_solve(RowShardedMatrixLinearOperator, ...) with GMRES (square) and LSMR (tall)
+    n = 1030
+    a, b, _ = gen.easy_problem(n, n, np.float32, spd=False)
+    bounds = lx._shard.shard_bounds(n, world)
+    lo, hi = bounds[rank], bounds[rank + 1]
+    op = RowShardedMatrixLinearOperator(torch.as_tensor(a[lo:hi]).cuda(), n)
+    sol = lx.linear_solve(op, torch.as_tensor(b[lo:hi]).cuda(), lx.GMRES(rtol=1e-6, atol=1e-6), throw=False)
+    xr, rr, st = oracle.gmres(a, b, 1e-6, 1e-6)
+    err = np.abs(sol.value.cpu().numpy() - xr[lo:hi]).max() / np.abs(xr).max()
+    good = int(sol.result) == rr and abs(int(sol.stats["num_steps"]) - st["num_steps"]) <= 2 and err < 1e-5
+    ok &= good
+    if rank == 0:
+        print(f"linear_solve(sharded, GMRES): result {int(sol.result)} steps {int(sol.stats['num_steps'])} "
+              f"err {err:.2e} -> {'OK' if good else 'FAIL'}")
+    m, n = 5000, 128
+    a, b, _ = gen.tall_lstsq(11, m, n, np.float32)
+    bounds = lx._shard.shard_bounds(m, world)
+    lo, hi = bounds[rank], bounds[rank + 1]
+    op = RowShardedMatrixLinearOperator(torch.as_tensor(a[lo:hi]).cuda(), m)
+    sol = lx.linear_solve(op, torch.as_tensor(b[lo:hi]).cuda(), lx.LSMR(rtol=1e-6, atol=1e-6), throw=False)
+    xr, rr, st = oracle.lsmr(a, b, 1e-6, 1e-6)
+    err = np.abs(sol.value.cpu().numpy() - xr).max() / np.abs(xr).max()
+    good = int(sol.result) == rr and abs(int(sol.stats["num_steps"]) - st["num_steps"]) <= 2 and err < 1e-5
+    ok &= good
+    if rank == 0:
+        print(f"linear_solve(sharded, LSMR): result {int(sol.result)} steps {int(sol.stats['num_steps'])} "
+              f"err {err:.2e} -> {'OK' if good else 'FAIL'}")
+    t = torch.tensor([1 if ok else 0], device="cuda")
+    dist.all_reduce(t, op=dist.ReduceOp.MIN)
+    if rank == 0:
+        print("DIST_QR_ALL_OK" if int(t.item()) == 1 else "DIST_QR_FAILED")
+    dist.destroy_process_group()
+    sys.exit(0 if int(t.item()) == 1 else 1)
+
+
+if __name__ == "__main__":
+    main()

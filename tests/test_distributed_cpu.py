@@ -245,3 +245,37 @@ def test_row_sharded_gmres_decomposition_world2_gloo(tmp_path):
     mp.spawn(_gmres_rows_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
     x0, x1 = np.load(tmp_path / "gmres0.npy"), np.load(tmp_path / "gmres1.npy")
     assert np.array_equal(x0, x1)
+
+
+def _tsqr_worker(rank, world, port, out_dir):
+    """RowShardedQR (TSQR) and its `lx.linear_solve(RowShardedMatrixLinearOperator, b_local, lx.QR())` entry on
+    a world-2 gloo group with the oracle-backed CPU doubles: local QR, all-gather of the R factors, small QR."""
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    import lineax_b200 as lx
+    from lineax_b200 import distributed as lxd
+    from oracle import gen
+    from tests import cpu_kernels
+
+    cpu_kernels.install()
+    lx.set_default_device("cpu")
+    m, n = 203, 17
+    a, b, _ = gen.tall_lstsq(9, m, n, np.float64)
+    solver = lxd.RowShardedQR(m, n, dtype=torch.float64, device="cpu")
+    lo, hi = solver.row_range()
+    x = solver.solve(torch.as_tensor(a[lo:hi]), torch.as_tensor(b[lo:hi]))
+    xl = np.linalg.lstsq(a, b, rcond=None)[0]
+    assert np.allclose(x.numpy(), xl, rtol=1e-10, atol=1e-12)
+    op = lxd.RowShardedMatrixLinearOperator(torch.as_tensor(a[lo:hi]), m)
+    op._solvers[("qr", m, n, torch.float64)] = solver
+    sol = lx.linear_solve(op, torch.as_tensor(b[lo:hi]), lx.QR(), throw=False)
+    assert np.allclose(sol.value.numpy(), xl, rtol=1e-10, atol=1e-12) and int(sol.result) == 0
+    np.save(os.path.join(out_dir, f"q{rank}.npy"), x.numpy())
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_row_sharded_tsqr_world2_gloo(tmp_path):
+    world = 2
+    mp.spawn(_tsqr_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    assert np.array_equal(np.load(tmp_path / "q0.npy"), np.load(tmp_path / "q1.npy")), "replicated bit for bit"
