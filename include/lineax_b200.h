@@ -189,6 +189,23 @@ LXB_DECL_DIAGTRI(f64, double)
 LXB_DECL_KRYLOV(f32, float)
 LXB_DECL_KRYLOV(f64, double)
 
+/* ------------------------------------------------ multi-RHS solves -------
+ * lineax/_solve.py:732-740 (`state=` reuse), 809-871 (`lx.invert`), and vmap(in_axes=(None, 0)) over
+ * `linear_solve`: `nrhs` vectors b[batch, nrhs, n] against ONE factorisation per system; x[batch, nrhs, n].
+ * Results are bit-identical to nrhs calls of the single-vector entry points.
+ */
+#define LXB_DECL_MULTI(sfx, T)                                                                       \
+  int lxb_lu_solve_multi_##sfx(const T* lu, int64_t stride_lu, const int32_t* piv, int64_t stride_piv, \
+                               const T* b, T* x, int64_t batch, int32_t n, int32_t nrhs, int32_t flags, \
+                               lxb_stream_t stream);                                                 \
+  int lxb_cholesky_solve_multi_##sfx(const T* factor, int64_t stride_f, const T* b, T* x,            \
+                                     int64_t batch, int32_t n, int32_t nrhs, int32_t flags,          \
+                                     lxb_stream_t stream);                                           \
+  int lxb_triangular_solve_multi_##sfx(const T* A, int64_t stride_A, const T* b, T* x, int64_t batch, \
+                                       int32_t n, int32_t nrhs, int32_t flags, lxb_stream_t stream);
+LXB_DECL_MULTI(f32, float)
+LXB_DECL_MULTI(f64, double)
+
 /* ------------------------------------------------ operator application --
  * MatrixLinearOperator.mv (lineax/_operator.py:265-269; LXB_TRANS -> A^T x),
  * DiagonalLinearOperator.mv (507-511), TridiagonalLinearOperator.mv (861-866;

@@ -67,6 +67,9 @@ for _sfx, _T in (("f32", c_float), ("f64", c_double)):
     _decl(f"lxb_diag_mv_{_sfx}", [P, c_int64, P, c_int64, P, c_int64, c_int32, P])
     _decl(f"lxb_tridiag_mv_{_sfx}", [P, P, P, c_int64, P, c_int64, P, c_int64, c_int32, P])
     _decl(f"lxb_norms_{_sfx}", [P, c_int64, P, c_int64, P, c_int64, c_int64, P])
+    _decl(f"lxb_lu_solve_multi_{_sfx}", [P, c_int64, P, c_int64, P, P, c_int64, c_int32, c_int32, c_int32, P])
+    _decl(f"lxb_cholesky_solve_multi_{_sfx}", [P, c_int64, P, P, c_int64, c_int32, c_int32, c_int32, P])
+    _decl(f"lxb_triangular_solve_multi_{_sfx}", [P, c_int64, P, P, c_int64, c_int32, c_int32, c_int32, P])
     _decl(f"lxb_gram_{_sfx}", [P, c_int64, P, c_int64, c_int32, c_int32, c_int32, P])
     _decl(f"lxb_cholesky_factor_{_sfx}", [P, c_int64, P, c_int64, c_int32, c_int32, P])
     _decl(f"lxb_cholesky_solve_{_sfx}", [P, c_int64, P, c_int64, P, c_int64, c_int32, c_int32, P])

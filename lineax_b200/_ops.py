@@ -84,6 +84,12 @@ def _define(name: str, fn, *, n_out: int, device_types="cuda"):
 
 
 # --------------------------------------------------------------------- LU ----
+def _use_multi(stride_factor: int, stride_b: int, nvec: int, n: int, dtype) -> bool:
+    """ONE factorisation against many vectors (vmap(in_axes=(None, 0)), `state=` reuse, `invert`): the
+    thread-per-vector multi-RHS kernels (csrc/multi_rhs.cu) read the factor once per tile of vectors."""
+    return stride_factor == 0 and stride_b == n and nvec >= 8 and n * 33 * dtype.itemsize <= 200 * 1024
+
+
 def _lu_factor(a: Tensor) -> Tuple[Tensor, Tensor]:
     _check_cuda(a)
     n = a.shape[-1]
@@ -110,6 +116,10 @@ def _lu_solve(lu: Tensor, piv: Tensor, b: Tensor, trans: bool) -> Tensor:
         piv_, s_p = _operand(piv, 1, full)
         b_, s_b = _operand(b.to(lu.dtype), 1, full)
         x = torch.empty(full + (n,), dtype=lu.dtype, device=lu.device)
+        if _use_multi(s_lu, s_b, B, n, lu.dtype) and s_p == 0:
+            nat.call(f"lxb_lu_solve_multi_{sfx}", lu_.data_ptr(), n * n, piv_.data_ptr(), n, b_.data_ptr(),
+                     x.data_ptr(), 1, n, B, nat.TRANS if trans else 0, _stream())
+            return x
         nat.call(f"lxb_lu_solve_{sfx}", lu_.data_ptr(), s_lu, piv_.data_ptr(), s_p, b_.data_ptr(), s_b,
                  x.data_ptr(), B, n, nat.TRANS if trans else 0, _stream())
     return x
@@ -441,6 +451,10 @@ def _cholesky_solve(f: Tensor, b: Tensor, nsd: bool) -> Tensor:
         f_, s_f = _operand(f, 2, full)
         b_, s_b = _operand(b.to(f.dtype), 1, full)
         x = torch.empty(full + (n,), dtype=f.dtype, device=f.device)
+        if _use_multi(s_f, s_b, math.prod(full), n, f.dtype):
+            nat.call(f"lxb_cholesky_solve_multi_{sfx}", f_.data_ptr(), n * n, b_.data_ptr(), x.data_ptr(), 1, n,
+                     math.prod(full), nat.NSD if nsd else 0, _stream())
+            return x
         nat.call(f"lxb_cholesky_solve_{sfx}", f_.data_ptr(), s_f, b_.data_ptr(), s_b, x.data_ptr(),
                  math.prod(full), n, nat.NSD if nsd else 0, _stream())
     return x
@@ -559,6 +573,10 @@ def _triangular_solve(a: Tensor, b: Tensor, lower: bool, unit: bool, trans: bool
         a_, s_a = _operand(a.to(dt), 2, full)
         b_, s_b = _operand(b.to(dt), 1, full)
         x = torch.empty(full + (n,), dtype=dt, device=a.device)
+        if _use_multi(s_a, s_b, math.prod(full), n, dt):
+            nat.call(f"lxb_triangular_solve_multi_{sfx}", a_.data_ptr(), n * n, b_.data_ptr(), x.data_ptr(), 1, n,
+                     math.prod(full), flags, _stream())
+            return x
         nat.call(f"lxb_triangular_solve_{sfx}", a_.data_ptr(), s_a, b_.data_ptr(), s_b, x.data_ptr(),
                  math.prod(full), n, flags, _stream())
     return x

@@ -146,3 +146,43 @@ def test_strided_and_odd_batches_tma_path():
     x_ref, _, _ = clib.lu_factor_solve(a[::2], b[::2])
     x, _, _ = _ops().lu_factor_solve(dev(a)[::2], dev(b)[::2], False)
     assert np.array_equal(host(x), x_ref)
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+@pytest.mark.parametrize("n", [5, 32, 100, 300, 700])
+@pytest.mark.parametrize("trans", [False, True])
+def test_multi_rhs_bit_identical_to_single_vector_solves(n, dtype, trans):
+    """`state=` reuse / `lx.invert` / vmap(in_axes=(None, 0)) (lineax/_solve.py:732-740, 809-871): many
+    vectors against ONE factorisation run the multi-RHS kernels (csrc/multi_rhs.cu) and must equal the
+    C oracle's getrs on every vector bit for bit."""
+    a, _, _ = gen.gaussian_systems(400 + n, 1, n, dtype)
+    rng = np.random.default_rng(n)
+    nrhs = 77
+    bs = rng.standard_normal((nrhs, n)).astype(dtype)
+    lu_ref, piv_ref = clib.lu_factor(a)
+    x_ref = clib.lu_solve(np.repeat(lu_ref, nrhs, 0), np.repeat(piv_ref, nrhs, 0), bs, trans=int(trans))
+    lu, piv = _ops().lu_factor(dev(a))
+    x = _ops().lu_solve(lu[0], piv[0], dev(bs), trans)  # unbatched factors, batched vectors
+    assert np.array_equal(host(x), x_ref)
+
+
+def test_multi_rhs_through_linear_solve_state_and_vmap():
+    """The public path: one `solver.init`, vmapped `linear_solve(..., state=state)` over 200 vectors."""
+    import lineax_b200 as lx
+
+    rng = np.random.default_rng(3)
+    n, nrhs = 64, 200
+    a = rng.standard_normal((n, n)) + 8 * np.eye(n)
+    bs = rng.standard_normal((nrhs, n))
+    A, Bs = dev(a), dev(bs)
+    for solver, op in ((lx.LU(), lx.MatrixLinearOperator(A)),
+                       (lx.Cholesky(), lx.MatrixLinearOperator(dev(a @ a.T), lx.positive_semidefinite_tag)),
+                       (lx.Triangular(), lx.MatrixLinearOperator(dev(np.triu(a)), lx.upper_triangular_tag))):
+        state = solver.init(op, {})
+        before = lx._native.launch_count()
+        xs = torch.func.vmap(lambda v: lx.linear_solve(op, v, solver, state=state, throw=False).value)(Bs)
+        torch.cuda.synchronize()
+        mat = op.as_matrix().cpu().numpy()
+        ref = np.linalg.solve(mat, bs.T).T
+        assert np.max(np.abs(host(xs) - ref)) / np.max(np.abs(ref)) < 1e-9, type(solver).__name__
+        assert lx._native.launch_count() - before <= 4, "one launch for all vectors, not one per vector"
