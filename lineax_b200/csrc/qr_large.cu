@@ -727,12 +727,21 @@ __device__ __forceinline__ void mma_tf32(uint32_t tmem_d, uint64_t da, uint64_t 
 }
 // byte offset of the 16-byte chunk `c` (0..7) of row `r` inside a swizzled 128 x 32 fp32 tile
 __device__ __forceinline__ int sw128(int r, int c) { return (r >> 3) * 1024 + (r & 7) * 128 + ((c ^ (r & 7)) << 4); }
+// x = hi + lo with BOTH parts rounded to nearest TF32 (cvt.rna): truncating them instead (the tensor core
+// ignores the 13 low mantissa bits of an fp32 operand) biases every product towards zero by ~2^-22, and
+// over a 262144-row contraction that bias does not average out (measured: ||R - R64||_F / ||R64||_F grew
+// linearly with n, 2.5e-6 at n = 2048, against 1e-7 with rounding).
+__device__ __forceinline__ float tf32_rn(float x) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  return __uint_as_float(r);
+}
 __device__ __forceinline__ void split_store(unsigned char* hi, unsigned char* lo, int r, int c, float4 x) {
   float4 h, l;
-  h.x = __uint_as_float(__float_as_uint(x.x) & 0xffffe000u); l.x = x.x - h.x;
-  h.y = __uint_as_float(__float_as_uint(x.y) & 0xffffe000u); l.y = x.y - h.y;
-  h.z = __uint_as_float(__float_as_uint(x.z) & 0xffffe000u); l.z = x.z - h.z;
-  h.w = __uint_as_float(__float_as_uint(x.w) & 0xffffe000u); l.w = x.w - h.w;
+  h.x = tf32_rn(x.x); l.x = tf32_rn(x.x - h.x);
+  h.y = tf32_rn(x.y); l.y = tf32_rn(x.y - h.y);
+  h.z = tf32_rn(x.z); l.z = tf32_rn(x.z - h.z);
+  h.w = tf32_rn(x.w); l.w = tf32_rn(x.w - h.w);
   *reinterpret_cast<float4*>(hi + sw128(r, c)) = h;
   *reinterpret_cast<float4*>(lo + sw128(r, c)) = l;
 }
@@ -1046,6 +1055,360 @@ __global__ void __launch_bounds__(kTcThreads, 3)
   if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(32));
 }
 
+// ------------------------------------------------------------ two-level blocking ----
+// With 32-column panels every trailing pass moves the whole trailing matrix through HBM three times for
+// 64 flops per element: 128 passes x 3 x ~2.1 GB = 0.8 TB per factorisation, a ~125 ms floor.
+// The fp32 path therefore groups FOUR panels into a 128-column outer block: inside the block the 32-wide
+// updates above touch at most 96 columns, and the trailing matrix is updated ONCE per outer block with
+// the 128 reflectors of the block, A2 <- A2 - V (T^T (V^T A2)), T = larft(V, taus) (128 x 128):
+//   qr_wbig_tc_kernel     W = V^T A2 on tcgen05 (3xTF32), M = 128 columns of A2, N = 128 reflectors, the
+//                         32-row chunks transposed while staged (both operands K-major), partial sums per
+//                         row group accumulated in TMEM; with MASKA the "A2" tile is the V block itself and
+//                         the kernel returns the Gram matrix G = V^T V the T factor needs
+//   qr_tbig_kernel        G = sum of the partials; T by LAPACK's larft recurrence T(0:i,i) = -tau_i T G(0:i,i)
+//   qr_wfinish128_kernel  W = sum of the row-group partials; Y = T^T W, stored TRANSPOSED (column-major in K)
+//                         so that it is a K-major B operand
+//   qr_update128_tc_kernel A2 -= V Y on tcgen05: 128-row x 64-column tiles, K = 128 as four staged 32-wide
+//                         chunks accumulated in one TMEM tile, the Y tile resident in shared memory
+namespace tc {
+constexpr uint32_t kIdesc64 = (1u << 4) | (2u << 7) | (2u << 10) | ((64u >> 3) << 17) | ((128u >> 4) << 24);  // N = 64
+__device__ __forceinline__ void mma_tf32_n64(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(tmem_d),
+      "l"(da), "l"(db), "r"(kIdesc64), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void mbar_wait_or_trap(uint64_t* mbar, uint32_t& phase) {
+  uint32_t done = 0;
+  for (int spin = 0; spin < (1 << 24) && !done; ++spin)
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}\n"
+                 : "=r"(done) : "r"(smem_u32(mbar)), "r"(phase) : "memory");
+  if (!done) __trap();  // bounded wait: fail loudly, never continue with stale TMEM
+  phase ^= 1;
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+        "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+        "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+}  // namespace tc
+
+constexpr int kOB = 128;  // outer block width (reflectors per trailing update)
+constexpr size_t kWbigSmem = 4 * 16384 + 1024 + 64;
+
+// Wp[grp][k][c] = sum over the rows of group grp of V[r][k] * A2[r][c], k < 128, c < ncols;
+// A2 = columns cbase0 .. cbase0 + ncols - 1 of `a` (MASKA: cbase0 == j0, the V block itself, masked).
+template <bool MASKA>
+__global__ void __launch_bounds__(kTcThreads, 2)
+    qr_wbig_tc_kernel(const float* __restrict__ a, float* __restrict__ Wp, int m, int n, int j0, int cbase0,
+                      int ncols, int ngroups) {
+  extern __shared__ unsigned char smem_dyn[];
+  unsigned char* base = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~(uintptr_t)1023);
+  unsigned char* Ahi = base;                  // 128 tile rows (A2 columns) x 128 B (32 rows of the chunk)
+  unsigned char* Alo = base + 16384;
+  unsigned char* Bhi = base + 2 * 16384;      // 128 tile rows (reflectors) x 128 B
+  unsigned char* Blo = base + 3 * 16384;
+  uint64_t* mbar = reinterpret_cast<uint64_t*>(base + 4 * 16384);
+  uint32_t* tslot = reinterpret_cast<uint32_t*>(base + 4 * 16384 + 16);
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const int tile = blockIdx.x, grp = blockIdx.y;
+  const int cbase = cbase0 + tile * 128;
+  const int cw = min(128, ncols - tile * 128);
+  const int rows_total = m - j0;
+  const int per = (((rows_total + ngroups - 1) / ngroups) + kWtcRows - 1) / kWtcRows * kWtcRows;
+  const int r0 = j0 + grp * per, r1 = min(m, r0 + per);
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tc::smem_u32(tslot)), "r"(128));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  if (tid == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(tc::smem_u32(mbar)));
+    asm volatile("fence.mbarrier_init.release.cluster;");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;");
+  const uint32_t tmem = *tslot;
+  const uint32_t a_hi = tc::smem_u32(Ahi), a_lo = tc::smem_u32(Alo), b_hi = tc::smem_u32(Bhi), b_lo = tc::smem_u32(Blo);
+  // staging map: a 32-row chunk of 128 columns = 8 row quads x 32 column quads of 4 x 4 blocks, two per thread
+  const int rq = tid & 7;
+  float4 pa[2][4], pv[2][4];
+  auto fetch = [&](int rb) {
+    const bool diag = rb < j0 + kOB;  // rows crossing the block's diagonal: unit diagonal, zeros above
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      const int cq = (tid >> 3) + 16 * i;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int gr = rb + 4 * rq + j;
+        float4 x = (gr < r1 && 4 * cq < cw) ? reinterpret_cast<const float4*>(a + (size_t)gr * n + cbase)[cq]
+                                            : make_float4(0.f, 0.f, 0.f, 0.f);
+        float4 v = gr < r1 ? reinterpret_cast<const float4*>(a + (size_t)gr * n + j0)[cq] : make_float4(0.f, 0.f, 0.f, 0.f);
+        if (diag && gr < r1) {
+          v.x = vmask<float>(v.x, gr, j0, 4 * cq);
+          v.y = vmask<float>(v.y, gr, j0, 4 * cq + 1);
+          v.z = vmask<float>(v.z, gr, j0, 4 * cq + 2);
+          v.w = vmask<float>(v.w, gr, j0, 4 * cq + 3);
+          if (MASKA) {
+            const int c0 = cbase - j0 + 4 * cq;
+            x.x = vmask<float>(x.x, gr, j0, c0);
+            x.y = vmask<float>(x.y, gr, j0, c0 + 1);
+            x.z = vmask<float>(x.z, gr, j0, c0 + 2);
+            x.w = vmask<float>(x.w, gr, j0, c0 + 3);
+          }
+        }
+        pa[i][j] = x;
+        pv[i][j] = v;
+      }
+    }
+  };
+  const int nchunks = r1 > r0 ? (r1 - r0 + kWtcRows - 1) / kWtcRows : 0;
+  uint32_t phase = 0;
+  // The tensor core accumulates into TMEM with truncation, so a long running sum there picks up a
+  // systematic bias (measured: ||R - R64||_F grew linearly with n when the whole row group was summed in
+  // TMEM).  Only ONE 32-row chunk (12 MMAs) is ever accumulated in TMEM; the running sum over the row group
+  // lives in fp32 registers (round-to-nearest adds), 128 per thread.
+  float acc[kOB];
+#pragma unroll
+  for (int k = 0; k < kOB; ++k) acc[k] = 0.f;
+  auto drain = [&]() {
+    tc::mbar_wait_or_trap(mbar, phase);
+    asm volatile("tcgen05.fence::after_thread_sync;");
+#pragma unroll
+    for (int qc = 0; qc < 4; ++qc) {
+      uint32_t r[32];
+      tc::tmem_ld32(tmem + ((uint32_t)(32 * warp) << 16) + 32 * qc, r);
+#pragma unroll
+      for (int k = 0; k < 32; ++k) acc[32 * qc + k] += __uint_as_float(r[k]);
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;");
+  };
+  if (nchunks > 0) fetch(r0);
+  for (int ch = 0; ch < nchunks; ++ch) {
+    if (ch > 0) drain();  // also frees the previous chunk's tiles and TMEM
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      tc::split_store_t(Ahi, Alo, 4 * ((tid >> 3) + 16 * i), rq, pa[i]);
+      tc::split_store_t(Bhi, Blo, 4 * ((tid >> 3) + 16 * i), rq, pv[i]);
+    }
+    if (ch + 1 < nchunks) fetch(r0 + (ch + 1) * kWtcRows);  // in flight while the MMAs run
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    __syncthreads();
+    if (tid == 0) {
+      asm volatile("tcgen05.fence::after_thread_sync;");
+#pragma unroll
+      for (int ks = 0; ks < kWtcRows / 8; ++ks) {
+        const uint64_t dah = tc::umma_desc(a_hi + 32 * ks), dal = tc::umma_desc(a_lo + 32 * ks);
+        const uint64_t dbh = tc::umma_desc(b_hi + 32 * ks), dbl = tc::umma_desc(b_lo + 32 * ks);
+        tc::mma_tf32(tmem, dal, dbh, ks > 0 ? 1u : 0u);  // small terms first
+        tc::mma_tf32(tmem, dah, dbl, 1u);
+        tc::mma_tf32(tmem, dah, dbh, 1u);
+      }
+      asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(tc::smem_u32(mbar)) : "memory");
+    }
+  }
+  if (nchunks > 0) drain();
+  // lane of TMEM = column of the A2 tile, TMEM column = reflector k
+  const int col = tile * 128 + tid;
+  if (tid < cw) {
+    float* out = Wp + ((size_t)grp * kOB) * ncols + col;
+#pragma unroll
+    for (int k = 0; k < kOB; ++k) out[(size_t)k * ncols] = acc[k];
+  }
+  __syncthreads();
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(128));
+}
+
+// G = V^T V from the row-group partials (ncols = 128), then T (128 x 128, upper triangular) by LAPACK's larft:
+// T(i,i) = tau_i, T(0:i, i) = -tau_i * T(0:i, 0:i) * G(0:i, i).  One CTA.
+constexpr int kTbigThreads = 512;
+__global__ void __launch_bounds__(kTbigThreads) qr_tbig_kernel(const float* __restrict__ Gp, const float* __restrict__ taus,
+                                                              float* __restrict__ Tb, int ngroups) {
+  extern __shared__ float tb_smem[];
+  float* G = tb_smem;                 // [128][129]
+  float* Ts = tb_smem + kOB * (kOB + 1);
+  const int tid = threadIdx.x;
+  for (int e = tid; e < kOB * kOB; e += kTbigThreads) {
+    const int k = e / kOB, c = e % kOB;
+    float s = 0.f;
+    for (int g = 0; g < ngroups; ++g) s += Gp[((size_t)g * kOB + k) * kOB + c];
+    G[k * (kOB + 1) + c] = s;
+    Ts[k * (kOB + 1) + c] = 0.f;
+  }
+  __syncthreads();
+  for (int i = 0; i < kOB; ++i) {
+    const float tau = taus[i];
+    float z = 0.f;
+    if (tid < i) {
+      for (int k = tid; k < i; ++k) z = fmaf(Ts[tid * (kOB + 1) + k], G[k * (kOB + 1) + i], z);
+    }
+    __syncthreads();
+    if (tid < i) Ts[tid * (kOB + 1) + i] = -tau * z;
+    if (tid == i) Ts[i * (kOB + 1) + i] = tau;
+    __syncthreads();
+  }
+  for (int e = tid; e < kOB * kOB; e += kTbigThreads) Tb[e] = Ts[(e / kOB) * (kOB + 1) + e % kOB];
+}
+
+// W = sum of the row-group partials; Yt[c][i] = sum_k T[k][i] W[k][c]  (Y = T^T W, stored K-major per column)
+constexpr int kWf128Cols = 32;
+__global__ void __launch_bounds__(256) qr_wfinish128_kernel(const float* __restrict__ Wp, const float* __restrict__ Tb,
+                                                            float* __restrict__ Yt, int ncols, int ngroups) {
+  __shared__ float Ws[kOB][kWf128Cols + 1];
+  const int tid = threadIdx.x, c0 = blockIdx.x * kWf128Cols;
+  for (int e = tid; e < kOB * kWf128Cols; e += 256) {
+    const int k = e / kWf128Cols, c = e % kWf128Cols;
+    float s = 0.f;
+    if (c0 + c < ncols)
+      for (int g = 0; g < ngroups; ++g) s += Wp[((size_t)g * kOB + k) * ncols + c0 + c];
+    Ws[k][c] = s;
+  }
+  __syncthreads();
+  for (int e = tid; e < kOB * kWf128Cols; e += 256) {
+    const int i = e % kOB, c = e / kOB;
+    if (c0 + c >= ncols) continue;
+    float y = 0.f;
+    for (int k = 0; k <= i; ++k) y = fmaf(Tb[k * kOB + i], Ws[k][c], y);
+    Yt[(size_t)(c0 + c) * kOB + i] = y;
+  }
+}
+
+// A2 -= V Y for the 128 reflectors of an outer block; Yt[c][k] (K-major per column).
+constexpr size_t kUp128Smem = 8 * 8192 + 2 * 16384 + 1024 + 64;
+__global__ void __launch_bounds__(kTcThreads, 2)
+    qr_update128_tc_kernel(float* __restrict__ a, const float* __restrict__ Yt, int m, int n, int j0, int ncols,
+                           int rblocks, int per_strip) {
+  extern __shared__ unsigned char smem_dyn[];
+  unsigned char* base = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~(uintptr_t)1023);
+  unsigned char* Bt = base;                   // 4 K-chunks x {hi, lo} x (64 columns x 128 B)
+  unsigned char* Ahi = base + 8 * 8192;       // 128 rows x 128 B (one K-chunk of V)
+  unsigned char* Alo = Ahi + 16384;
+  uint64_t* mbar = reinterpret_cast<uint64_t*>(Alo + 16384);
+  uint32_t* tslot = reinterpret_cast<uint32_t*>(Alo + 16384 + 16);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int tile = blockIdx.x;
+  const int cbase = j0 + kOB + tile * 64;
+  const int cw = min(64, ncols - tile * 64);
+  const int b0 = blockIdx.y * per_strip, b1 = min(rblocks, b0 + per_strip);
+  if (b0 >= b1) return;  // uniform per CTA, before any allocation
+  if (warp == 0) {
+    // four accumulators of 64 columns, one per K-chunk: TMEM accumulation truncates, so no sum there is
+    // longer than the 12 MMAs of one chunk; the four are added in registers (round to nearest)
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tc::smem_u32(tslot)), "r"(256));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  if (tid == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(tc::smem_u32(mbar)));
+    asm volatile("fence.mbarrier_init.release.cluster;");
+  }
+  // Y tile: tile row = column of A2 (N index), 128 B of K per chunk
+#pragma unroll 4
+  for (int i = 0; i < 16; ++i) {
+    const int idx = tid + 128 * i, q = idx & 7, c = (idx >> 3) & 63, kc = idx >> 9;
+    const float4 y = c < cw ? reinterpret_cast<const float4*>(Yt + (size_t)(tile * 64 + c) * kOB + 32 * kc)[q]
+                            : make_float4(0.f, 0.f, 0.f, 0.f);
+    tc::split_store(Bt + (2 * kc) * 8192, Bt + (2 * kc + 1) * 8192, c, q, y);
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;");
+  const uint32_t tmem = *tslot;
+  const uint32_t a_hi = tc::smem_u32(Ahi), a_lo = tc::smem_u32(Alo), b_t = tc::smem_u32(Bt);
+  uint32_t phase = 0;
+  for (int b = b0; b < b1; ++b) {
+    const int rb = j0 + b * 128;
+#pragma unroll 1
+    for (int kc = 0; kc < 4; ++kc) {
+      // V chunk kc of this row block: 8 lanes per row (one 16-byte chunk each), 16 rows per sweep
+      float4 v[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int r = (tid >> 3) + 16 * i, c = tid & 7, gr = rb + r;
+        v[i] = gr < m ? reinterpret_cast<const float4*>(a + (size_t)gr * n + j0 + 32 * kc)[c] : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+      if (kc > 0) tc::mbar_wait_or_trap(mbar, phase);  // the previous chunk's MMAs have read the A tiles
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int r = (tid >> 3) + 16 * i, c = tid & 7, gr = rb + r;
+        if (b == 0) {  // rows crossing the block's diagonal: unit diagonal, zeros above
+          v[i].x = vmask<float>(v[i].x, gr, j0, 32 * kc + 4 * c);
+          v[i].y = vmask<float>(v[i].y, gr, j0, 32 * kc + 4 * c + 1);
+          v[i].z = vmask<float>(v[i].z, gr, j0, 32 * kc + 4 * c + 2);
+          v[i].w = vmask<float>(v[i].w, gr, j0, 32 * kc + 4 * c + 3);
+        }
+        tc::split_store(Ahi, Alo, r, c, v[i]);
+      }
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      __syncthreads();
+      if (tid == 0) {
+        asm volatile("tcgen05.fence::after_thread_sync;");
+        const uint32_t b_hi = b_t + (2 * kc) * 8192, b_lo = b_t + (2 * kc + 1) * 8192;
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks) {
+          const uint64_t dah = tc::umma_desc(a_hi + 32 * ks), dal = tc::umma_desc(a_lo + 32 * ks);
+          const uint64_t dbh = tc::umma_desc(b_hi + 32 * ks), dbl = tc::umma_desc(b_lo + 32 * ks);
+          tc::mma_tf32_n64(tmem + 64 * kc, dal, dbh, ks > 0 ? 1u : 0u);
+          tc::mma_tf32_n64(tmem + 64 * kc, dah, dbl, 1u);
+          tc::mma_tf32_n64(tmem + 64 * kc, dah, dbh, 1u);
+        }
+        asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(tc::smem_u32(mbar)) : "memory");
+      }
+    }
+    tc::mbar_wait_or_trap(mbar, phase);
+    asm volatile("tcgen05.fence::after_thread_sync;");
+    // epilogue: as in qr_update_tc_kernel, 32 x 32 chunks turned around in (dead) A tiles
+    float4* S = reinterpret_cast<float4*>(Ahi + warp * 4096);
+#pragma unroll 1
+    for (int qc = 0; qc < 2; ++qc) {
+      float p32[32];
+      {
+        uint32_t r[32];
+        tc::tmem_ld32(tmem + ((uint32_t)(32 * warp) << 16) + 32 * qc, r);
+#pragma unroll
+        for (int k = 0; k < 32; ++k) p32[k] = __uint_as_float(r[k]);
+#pragma unroll
+        for (int kc = 1; kc < 4; ++kc) {
+          tc::tmem_ld32(tmem + ((uint32_t)(32 * warp) << 16) + 64 * kc + 32 * qc, r);
+#pragma unroll
+          for (int k = 0; k < 32; ++k) p32[k] += __uint_as_float(r[k]);
+        }
+      }
+      __syncwarp();
+#pragma unroll
+      for (int g4 = 0; g4 < 8; ++g4)
+        S[lane * 8 + (g4 ^ (lane & 7))] = make_float4(p32[4 * g4], p32[4 * g4 + 1], p32[4 * g4 + 2], p32[4 * g4 + 3]);
+      __syncwarp();
+      const int c = lane & 7, col = 32 * qc + 4 * c;
+      float4 x[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int rr = 4 * i + (lane >> 3), gr = rb + 32 * warp + rr;
+        if (gr < m && col < cw) x[i] = *reinterpret_cast<const float4*>(a + (size_t)gr * n + cbase + col);
+      }
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int rr = 4 * i + (lane >> 3), gr = rb + 32 * warp + rr;
+        if (gr < m && col < cw) {
+          const float4 p = S[rr * 8 + (c ^ (rr & 7))];
+          x[i].x -= p.x; x[i].y -= p.y; x[i].z -= p.z; x[i].w -= p.w;
+          *reinterpret_cast<float4*>(a + (size_t)gr * n + cbase + col) = x[i];
+        }
+      }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;");
+    __syncthreads();  // TMEM and the A tiles are free for the next block
+  }
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(256));
+}
+
 // --------------------------------------------------- apply Q^T to one vector ----
 // y <- H_n ... H_2 H_1 y, one 32-reflector block at a time with TWO grid barriers per block
 // (instead of one per reflector).  For block V (unit lower trapezoidal, taus t):
@@ -1242,7 +1605,7 @@ __global__ void __launch_bounds__(1024) qr_rsolve_kernel(const T* __restrict__ a
 template <typename T>
 struct QrLargePlan {
   int nb, nb_panel, rows_cta;
-  size_t smem_panel, ws_bytes, wp_off, w2_off, t_off, gpart_off, gfull_off, y_off;
+  size_t smem_panel, ws_bytes, wp_off, w2_off, t_off, gpart_off, gfull_off, y_off, tbig_off, yt_off;
   int ngroups, in_smem;
   bool ok;
 };
@@ -1270,6 +1633,8 @@ QrLargePlan<T> qr_large_plan(int m, int n) {
   pl.wp_off = off; off += (size_t)pl.ngroups * kPB * pad4(n);
   pl.w2_off = off; off += (size_t)kPB * pad4(n);
   pl.y_off = off; off += pad4(m);
+  pl.tbig_off = off; off += (size_t)kOB * kOB;        // T of an outer block (two-level blocking)
+  pl.yt_off = off; off += (size_t)kOB * pad4(n);      // Y = T^T W, transposed
   pl.ws_bytes = off * sizeof(T);
   pl.ok = true;
   return pl;
@@ -1294,15 +1659,18 @@ int qr_large_factor(const T* A, T* a, T* taus, int m, int n, void* ws, size_t ws
   T* Tm = w + pl.t_off;
   T* Wp = w + pl.wp_off;
   T* W2 = w + pl.w2_off;
-  for (int j0 = 0; j0 < n; j0 += kPB) {
-    int nbw = n - j0 < kPB ? n - j0 : kPB;
-    int mm = m, nn = n, jj0 = j0;
+  // one 32-column panel at column jp
+  auto run_panel = [&](int jp) -> int {
+    int nbw = n - jp < kPB ? n - jp : kPB;
+    int mm = m, nn = n, jj0 = jp;
     void* args[] = {&a, &taus, &Tm, &part, &gpart, &gfull, &mm, &nn, &jj0, &nbw};
     LXB_CUDA_TRY(cudaLaunchCooperativeKernel((const void*)pk, dim3(pl.nb_panel), dim3(kPanelThreads), args,
                                              pl.smem_panel, st));
     count_launch();
-    const int ncols = n - j0 - kPB;
-    if (ncols <= 0) break;
+    return 0;
+  };
+  // apply the block reflector of the panel at j0 (T in Tm) to the `ncols` columns that follow it
+  auto trail32 = [&](int j0, int ncols) -> int {
     const int tiles = (ncols + kUpCols - 1) / kUpCols;
 #ifdef LXB_QR_WTC_EXPERIMENT  // tcgen05 W = V^T A2: compile-time opt-in until its in-situ parity run is green
     static const bool use_wtc = [] { const char* e = getenv("LXB_QR_WTC"); return e && atoi(e) == 1; }();
@@ -1361,6 +1729,77 @@ int qr_large_factor(const T* A, T* a, T* taus, int m, int n, void* ws, size_t ws
       qr_update_simple_kernel<T><<<dim3(tiles, rblocks), 256, u_smem, st>>>(a, W2, m, n, j0, ncols);
     }
     LXB_CUDA_CHECK_LAUNCH();
+    return 0;
+  };
+  // Two-level blocking (fp32, aligned): four panels per 128-column outer block, the trailing matrix is
+  // updated once per outer block with K = 128 on the tensor cores (kernels above).  LXB_QR_TWOLEVEL=0
+  // restores the panel-by-panel trailing updates.
+  static const bool two_level_env = [] { const char* e = getenv("LXB_QR_TWOLEVEL"); return !(e && atoi(e) == 0); }();
+  bool two_level = false;
+  if constexpr (sizeof(T) == 4) {
+    two_level = two_level_env && (n % 4 == 0) && ((reinterpret_cast<uintptr_t>(a) & 15) == 0) && n > kOB;
+  }
+  if (!two_level) {
+    for (int j0 = 0; j0 < n; j0 += kPB) {
+      int rc = run_panel(j0);
+      if (rc) return rc;
+      const int ncols = n - j0 - kPB;
+      if (ncols <= 0) break;
+      rc = trail32(j0, ncols);
+      if (rc) return rc;
+    }
+    return 0;
+  }
+  if constexpr (sizeof(T) == 4) {
+    float* af = reinterpret_cast<float*>(a);
+    float* Wpf = reinterpret_cast<float*>(Wp);
+    float* Tb = reinterpret_cast<float*>(w + pl.tbig_off);
+    float* Yt = reinterpret_cast<float*>(w + pl.yt_off);
+    LXB_CUDA_TRY(cudaFuncSetAttribute(qr_wbig_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kWbigSmem));
+    LXB_CUDA_TRY(cudaFuncSetAttribute(qr_wbig_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kWbigSmem));
+    LXB_CUDA_TRY(cudaFuncSetAttribute(qr_update128_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kUp128Smem));
+    const size_t tb_smem = (size_t)2 * kOB * (kOB + 1) * sizeof(float);
+    LXB_CUDA_TRY(cudaFuncSetAttribute(qr_tbig_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tb_smem));
+    const size_t wp_cap = (size_t)pl.ngroups * kPB * pad4(n);  // elements reserved for row-group partials
+    for (int j0 = 0; j0 < n; j0 += kOB) {
+      const int jend = j0 + kOB < n ? j0 + kOB : n;
+      for (int jp = j0; jp < jend; jp += kPB) {
+        int rc = run_panel(jp);
+        if (rc) return rc;
+        const int inner = jend - jp - kPB;
+        if (inner > 0) {
+          rc = trail32(jp, inner);
+          if (rc) return rc;
+        }
+      }
+      const int ncols = n - jend;
+      if (ncols <= 0) break;
+      // T of the 128 reflectors: Gram matrix on the tensor cores, larft recurrence in one CTA
+      int gg = (int)(wp_cap / ((size_t)kOB * kOB));
+      gg = gg > 64 ? 64 : gg;
+      qr_wbig_tc_kernel<true><<<dim3(1, gg), kTcThreads, kWbigSmem, st>>>(af, Wpf, m, n, j0, j0, kOB, gg);
+      LXB_CUDA_CHECK_LAUNCH();
+      qr_tbig_kernel<<<1, kTbigThreads, tb_smem, st>>>(Wpf, reinterpret_cast<const float*>(taus) + j0, Tb, gg);
+      LXB_CUDA_CHECK_LAUNCH();
+      // W = V^T A2 (row-group partials), Y = T^T W, A2 -= V Y
+      const int wt = (ncols + 127) / 128;
+      int ng = (6 * kNumSMs + wt - 1) / wt;
+      const int cap = (int)(wp_cap / ((size_t)kOB * ncols));
+      ng = ng > cap ? cap : ng;
+      ng = ng > kW2MaxGroups ? kW2MaxGroups : (ng < 1 ? 1 : ng);
+      qr_wbig_tc_kernel<false><<<dim3(wt, ng), kTcThreads, kWbigSmem, st>>>(af, Wpf, m, n, j0, jend, ncols, ng);
+      LXB_CUDA_CHECK_LAUNCH();
+      qr_wfinish128_kernel<<<(ncols + kWf128Cols - 1) / kWf128Cols, 256, 0, st>>>(Wpf, Tb, Yt, ncols, ng);
+      LXB_CUDA_CHECK_LAUNCH();
+      const int ut = (ncols + 63) / 64;
+      const int rblocks = (m - j0 + 127) / 128;
+      int strips = (4 * 2 * kNumSMs + ut - 1) / ut;
+      strips = strips < 1 ? 1 : (strips > rblocks ? rblocks : strips);
+      const int per_strip = (rblocks + strips - 1) / strips;
+      strips = (rblocks + per_strip - 1) / per_strip;
+      qr_update128_tc_kernel<<<dim3(ut, strips), kTcThreads, kUp128Smem, st>>>(af, Yt, m, n, j0, ncols, rblocks, per_strip);
+      LXB_CUDA_CHECK_LAUNCH();
+    }
   }
   return 0;
 }

@@ -158,7 +158,8 @@ def test_diagonal_and_triangular(dtype):
 @pytest.mark.parametrize("shape,dtype", [((4096, 256), np.float32), ((8192, 130), np.float64),
                                           ((20000, 96), np.float32), ((65536, 64), np.float32),
                                           ((8192, 131), np.float32), ((6000, 67), np.float64),
-                                          ((16384, 640), np.float32), ((300000, 64), np.float32)])
+                                          ((16384, 640), np.float32), ((300000, 64), np.float32),
+                                          ((10000, 300), np.float32), ((9000, 132), np.float32)])
 def test_qr_large_blocked(shape, dtype):
     """Blocked (compact WY) Householder QR on all SMs for one large tall matrix: same R / taus as
     LAPACK geqrf (identical sign conventions) and the least-squares solution of qr.py:89-92."""
