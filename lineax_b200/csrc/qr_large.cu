@@ -1173,9 +1173,11 @@ __global__ void __launch_bounds__(kTcThreads, 2)
   const int nchunks = r1 > r0 ? (r1 - r0 + kWtcRows - 1) / kWtcRows : 0;
   uint32_t phase = 0;
   // The tensor core accumulates into TMEM with truncation, so a long running sum there picks up a
-  // systematic bias (measured: ||R - R64||_F grew linearly with n when the whole row group was summed in
-  // TMEM).  Only ONE 32-row chunk (12 MMAs) is ever accumulated in TMEM; the running sum over the row group
-  // lives in fp32 registers (round-to-nearest adds), 128 per thread.
+  // systematic bias (measured: ||R - R64||_F / ||R64||_F = 2.5e-6 at n = 2048, growing linearly with n, when
+  // a whole row group -- ~280 chunks -- was summed in TMEM; 7e-8 with short sums).  At most kDrainEvery
+  // 32-row chunks (48 MMAs) are accumulated in TMEM; the running sum over the row group lives in fp32
+  // registers (round-to-nearest adds), 128 per thread.
+  constexpr int kDrainEvery = 4;
   float acc[kOB];
 #pragma unroll
   for (int k = 0; k < kOB; ++k) acc[k] = 0.f;
@@ -1193,7 +1195,11 @@ __global__ void __launch_bounds__(kTcThreads, 2)
   };
   if (nchunks > 0) fetch(r0);
   for (int ch = 0; ch < nchunks; ++ch) {
-    if (ch > 0) drain();  // also frees the previous chunk's tiles and TMEM
+    const bool fresh = ch % kDrainEvery == 0;  // this chunk starts a new TMEM sum
+    if (ch > 0) {
+      if (fresh) drain();                              // wait + add the finished TMEM sum to the registers
+      else tc::mbar_wait_or_trap(mbar, phase);         // wait only: the previous chunk's tiles are free
+    }
 #pragma unroll
     for (int i = 0; i < 2; ++i) {
       tc::split_store_t(Ahi, Alo, 4 * ((tid >> 3) + 16 * i), rq, pa[i]);
@@ -1208,7 +1214,7 @@ __global__ void __launch_bounds__(kTcThreads, 2)
       for (int ks = 0; ks < kWtcRows / 8; ++ks) {
         const uint64_t dah = tc::umma_desc(a_hi + 32 * ks), dal = tc::umma_desc(a_lo + 32 * ks);
         const uint64_t dbh = tc::umma_desc(b_hi + 32 * ks), dbl = tc::umma_desc(b_lo + 32 * ks);
-        tc::mma_tf32(tmem, dal, dbh, ks > 0 ? 1u : 0u);  // small terms first
+        tc::mma_tf32(tmem, dal, dbh, (!fresh || ks > 0) ? 1u : 0u);  // small terms first
         tc::mma_tf32(tmem, dah, dbl, 1u);
         tc::mma_tf32(tmem, dah, dbh, 1u);
       }
@@ -1225,6 +1231,20 @@ __global__ void __launch_bounds__(kTcThreads, 2)
   }
   __syncthreads();
   if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(128));
+}
+
+// G = sum of the row-group partials of the Gram kernel (fixed order, 8 loads in flight per thread)
+__global__ void __launch_bounds__(256) qr_gsum_kernel(const float* __restrict__ Gp, float* __restrict__ G, int ngroups) {
+  const int e = blockIdx.x * 256 + threadIdx.x;
+  float s = 0.f;
+  for (int g0 = 0; g0 < ngroups; g0 += 8) {
+    float t[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) t[u] = g0 + u < ngroups ? Gp[(size_t)(g0 + u) * kOB * kOB + e] : 0.f;
+#pragma unroll
+    for (int u = 0; u < 8; ++u) s += t[u];
+  }
+  G[e] = s;
 }
 
 // G = V^T V from the row-group partials (ncols = 128), then T (128 x 128, upper triangular) by LAPACK's larft:
@@ -1323,17 +1343,34 @@ __global__ void __launch_bounds__(kTcThreads, 2)
   const uint32_t tmem = *tslot;
   const uint32_t a_hi = tc::smem_u32(Ahi), a_lo = tc::smem_u32(Alo), b_t = tc::smem_u32(Bt);
   uint32_t phase = 0;
+  // The CTA is latency bound on its global loads (ncu: long_scoreboard 52 %, 8 warps per SM), so (i) the
+  // next row block's V rows and A2 tile are pulled into L2 one block ahead and (ii) the V chunk of step
+  // kc + 1 is loaded into registers while the MMAs of step kc run.
+  auto prefetch_block = [&](int bb) {
+    const int prb = j0 + bb * 128;
+    if (prb + tid < m) {
+      const float* vr = a + (size_t)(prb + tid) * n + j0;
+#pragma unroll
+      for (int l = 0; l < 4; ++l) asm volatile("prefetch.global.L2 [%0];" ::"l"(vr + 32 * l));
+      if (cw > 0) asm volatile("prefetch.global.L2 [%0];" ::"l"(a + (size_t)(prb + tid) * n + cbase));
+      if (cw > 32) asm volatile("prefetch.global.L2 [%0];" ::"l"(a + (size_t)(prb + tid) * n + cbase + 32));
+    }
+  };
+  auto load_v = [&](int rb, int kc, float4 (&v)[8]) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int r = (tid >> 3) + 16 * i, c = tid & 7, gr = rb + r;
+      v[i] = gr < m ? reinterpret_cast<const float4*>(a + (size_t)gr * n + j0 + 32 * kc)[c] : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+  };
+  prefetch_block(b0);
+  float4 v[8];
+  load_v(j0 + b0 * 128, 0, v);
   for (int b = b0; b < b1; ++b) {
     const int rb = j0 + b * 128;
+    if (b + 1 < b1) prefetch_block(b + 1);
 #pragma unroll 1
     for (int kc = 0; kc < 4; ++kc) {
-      // V chunk kc of this row block: 8 lanes per row (one 16-byte chunk each), 16 rows per sweep
-      float4 v[8];
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const int r = (tid >> 3) + 16 * i, c = tid & 7, gr = rb + r;
-        v[i] = gr < m ? reinterpret_cast<const float4*>(a + (size_t)gr * n + j0 + 32 * kc)[c] : make_float4(0.f, 0.f, 0.f, 0.f);
-      }
       if (kc > 0) tc::mbar_wait_or_trap(mbar, phase);  // the previous chunk's MMAs have read the A tiles
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
@@ -1346,6 +1383,9 @@ __global__ void __launch_bounds__(kTcThreads, 2)
         }
         tc::split_store(Ahi, Alo, r, c, v[i]);
       }
+      // next chunk (or the first chunk of the next row block) in flight while the tensor core works
+      if (kc < 3) load_v(rb, kc + 1, v);
+      else if (b + 1 < b1) load_v(rb + 128, 0, v);
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
       __syncthreads();
       if (tid == 0) {
@@ -1682,7 +1722,10 @@ int qr_large_factor(const T* A, T* a, T* taus, int m, int n, void* ws, size_t ws
     // row groups: about two waves of CTAs at the kernel's occupancy, whatever the tile count is
     const int wocc = sizeof(T) == 4 ? 4 : 2;
     int ngroups = (2 * wocc * kNumSMs + wtiles - 1) / wtiles;
-    ngroups = ngroups < 16 ? 16 : (ngroups > kW2MaxGroups ? kW2MaxGroups : ngroups);
+    // (the partial buffer holds kW2MaxGroups x 32 x n elements: narrow updates -- the inner updates of the
+    //  two-level blocking, <= 96 columns -- may use more row groups than wide ones)
+    const int gcap = (int)std::min<size_t>(4 * kNumSMs, (size_t)kW2MaxGroups * pad4(n) / (size_t)ncols);
+    ngroups = ngroups < 16 ? 16 : (ngroups > gcap ? gcap : ngroups);
     if (w_tc) {
       LXB_CUDA_TRY(cudaFuncSetAttribute(qr_wpartial_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kWtcSmem));
       int* errp = reinterpret_cast<int*>(w + pl.gfull_off + kPB * kPB + kPB);
@@ -1776,10 +1819,12 @@ int qr_large_factor(const T* A, T* a, T* taus, int m, int n, void* ws, size_t ws
       if (ncols <= 0) break;
       // T of the 128 reflectors: Gram matrix on the tensor cores, larft recurrence in one CTA
       int gg = (int)(wp_cap / ((size_t)kOB * kOB));
-      gg = gg > 64 ? 64 : gg;
+      gg = gg > 2 * kNumSMs ? 2 * kNumSMs : gg;
       qr_wbig_tc_kernel<true><<<dim3(1, gg), kTcThreads, kWbigSmem, st>>>(af, Wpf, m, n, j0, j0, kOB, gg);
       LXB_CUDA_CHECK_LAUNCH();
-      qr_tbig_kernel<<<1, kTbigThreads, tb_smem, st>>>(Wpf, reinterpret_cast<const float*>(taus) + j0, Tb, gg);
+      qr_gsum_kernel<<<kOB * kOB / 256, 256, 0, st>>>(Wpf, Yt, gg);  // G parked in the (still unused) Y buffer
+      LXB_CUDA_CHECK_LAUNCH();
+      qr_tbig_kernel<<<1, kTbigThreads, tb_smem, st>>>(Yt, reinterpret_cast<const float*>(taus) + j0, Tb, 1);
       LXB_CUDA_CHECK_LAUNCH();
       // W = V^T A2 (row-group partials), Y = T^T W, A2 -= V Y
       const int wt = (ncols + 127) / 128;
