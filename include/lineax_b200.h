@@ -257,6 +257,21 @@ LXB_DECL_GRAM(f64, double)
 LXB_DECL_GMRES_DIST(f32, float)
 LXB_DECL_GMRES_DIST(f64, double)
 
+/* CG (lineax/_solver/cg.py:114-227, no preconditioner) on ONE SPD system partitioned by rows like the
+ * row-sharded GMRES above: same arguments, the symmetric buffer has lxb_gmres_rowsharded_symm_bytes_* bytes.
+ * Three fused exchange rounds per iteration (all-gather of p, <Ap, p>, {<r, r>, the two max-norms}).
+ */
+#define LXB_DECL_CG_DIST(sfx, T)                                                                    \
+  int lxb_cg_rowsharded_##sfx(const T* A_local, const T* b_local, T* x_local, int32_t* result,      \
+                              int32_t* num_steps, int32_t n, int32_t n_local, int32_t row_offset,   \
+                              T rtol, T atol, int32_t max_steps, int32_t stabilise_every,           \
+                              int32_t flags, void* workspace, size_t workspace_bytes,               \
+                              void* const* peer_buffers, int32_t world, int32_t rank,               \
+                              lxb_stream_t stream);                                                 \
+  size_t lxb_cg_rowsharded_workspace_##sfx(int32_t n_local);
+LXB_DECL_CG_DIST(f32, float)
+LXB_DECL_CG_DIST(f64, double)
+
 /* LSMR (lineax/_solver/lsmr.py:94-409) on ONE tall system partitioned by ROWS over the GPUs of an
  * NVLink box: rank r owns m_local contiguous rows of A (A_local[m_local, n] row-major, 16-byte
  * aligned) and the same slice of b; the solution x[n] and the statistics are replicated (every

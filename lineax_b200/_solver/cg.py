@@ -41,6 +41,12 @@ class CG(AbstractLinearSolver):
             raise NotImplementedError("the native CG kernel implements the default `max_norm` test")
 
     def init(self, operator, options):
+        from .gmres import _is_row_sharded
+
+        if _is_row_sharded(operator):  # tags of a sharded operator are the caller's word (`operator.tags`)
+            if operator.rows != operator.cols:
+                raise ValueError("`CG()` may only be used for linear solves with square matrices.")
+            return operator, bool(getattr(operator, "is_nsd", False))
         del options
         is_nsd = is_negative_semidefinite(operator)
         if not tr.structure_equal(operator.in_structure(), operator.out_structure()):
@@ -54,6 +60,20 @@ class CG(AbstractLinearSolver):
 
     def compute(self, state, vector, options):
         operator, is_nsd = state
+        from .gmres import _is_row_sharded
+
+        if _is_row_sharded(operator):
+            from ..distributed import RowShardedCG
+
+            if options.get("preconditioner") is not None:
+                raise NotImplementedError("row-sharded CG takes no preconditioner")
+            key = (operator.rows, float(self.rtol), float(self.atol), self.stabilise_every, self.max_steps, is_nsd,
+                   operator.local.dtype)
+            solver = operator.sharded_solver("cg", key, lambda: RowShardedCG(
+                operator.rows, float(self.rtol), float(self.atol), stabilise_every=self.stabilise_every,
+                max_steps=self.max_steps, is_nsd=is_nsd, dtype=operator.local.dtype, group=operator.group))
+            x, result, steps = solver.solve(operator.local, vector, options.get("y0"))
+            return x, result, {"num_steps": steps, "max_steps": self.max_steps}
         preconditioner, y0 = preconditioner_and_y0(operator, vector, options)
         if preconditioner is not None and not is_positive_semidefinite(preconditioner):
             raise ValueError("The preconditioner must be positive definite.")
