@@ -752,7 +752,7 @@ constexpr size_t kTcSmem = 4 * 16384 + 1024 /* alignment slack */ + 64;
 
 __global__ void __launch_bounds__(kTcThreads)
     qr_update_tc_kernel(float* __restrict__ a, const float* __restrict__ W2, int m, int n, int j0, int ncols,
-                        int rblocks, int per_strip, int* __restrict__ err) {
+                        int rblocks, int per_strip) {
   extern __shared__ unsigned char smem_dyn[];
   unsigned char* base = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~(uintptr_t)1023);
   unsigned char* Bhi = base;
@@ -895,28 +895,14 @@ __global__ void __launch_bounds__(kTcThreads)
   if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(128));
 }
 
-// Tensor-core variant of W = V^T A2 (fp32, aligned rows; OPT-IN with LXB_QR_WTC=1), same 3xTF32 split.
-// Per CTA: a 128-column tile of A2 and one row group.  The contraction runs over the ROWS; the chunks are
-// TRANSPOSED while they are staged so that both operands are K-major, the configuration of the update
-// kernel (an MN-major encoding of the untransposed chunks returned zeros: tools/tc_mn_major_probe.cu):
-//   A operand (M = 128 columns of A2, K = 32 rows): tile row = A2 column, 128-byte swizzled rows
-//   B operand (N = 32 panel columns, K = 32 rows):  tile row = panel column
-//   D (128 lanes x 32 TMEM columns) holds one chunk's product; the sum over the row group is kept in
-//   fp32 registers.
-// Staging: thread (rq = tid & 7, cq) loads a 4 x 4 block (rows 4rq.., columns 4cq..), transposes it in
-// registers and stores four 16-byte K-chunks; a quarter warp covers the 8 chunks of one tile row, so the
-// stores are conflict free.  The next chunk is in registers (loads in flight) while the tensor core works.
-// Status: the staging + MMA configuration is verified in the standalone probe (max err 7e-9 at |W| = 6e-3
-// for 1 .. 64 chunks); the in-situ parity run is still to be done, hence opt-in.
+// Transposed staging for the W = V^T A2 product on tcgen05 (qr_wbig_tc_kernel below): the contraction runs
+// over the ROWS, so the 32-row chunks are TRANSPOSED while they are staged and both operands become K-major,
+// the configuration of the update kernels (an MN-major encoding of the untransposed chunks returned zeros:
+// tools/tc_mn_major_probe.cu).  Thread (rq = tid & 7, cq) loads a 4 x 4 block (rows 4rq.., columns 4cq..),
+// transposes it in registers and stores four 16-byte K-chunks; a quarter warp covers the 8 chunks of one
+// tile row, so the stores are conflict free.  (A K = 32 version of this kernel, one panel at a time, was
+// validated in situ this round and measured no faster than the SIMT W kernel -- 317 vs 313 ms -- and removed.)
 namespace tc {
-constexpr uint32_t kIdescW = (1u << 4) | (2u << 7) | (2u << 10) | ((32u >> 3) << 17) | ((128u >> 4) << 24);  // K-major, M = 128, N = 32
-__device__ __forceinline__ void mma_tf32_w(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(tmem_d),
-      "l"(da), "l"(db), "r"(kIdescW), "r"(accumulate)
-      : "memory");
-}
 __device__ __forceinline__ void split_store_t(unsigned char* hi, unsigned char* lo, int col0, int rq, const float4 (&x)[4]) {
   split_store(hi, lo, col0 + 0, rq, make_float4(x[0].x, x[1].x, x[2].x, x[3].x));
   split_store(hi, lo, col0 + 1, rq, make_float4(x[0].y, x[1].y, x[2].y, x[3].y));
@@ -926,134 +912,6 @@ __device__ __forceinline__ void split_store_t(unsigned char* hi, unsigned char* 
 }  // namespace tc
 
 constexpr int kWtcRows = 32;  // rows per chunk
-constexpr size_t kWtcSmem = 2 * 16384 + 2 * 4096 + 1024 + 64;
-
-__global__ void __launch_bounds__(kTcThreads, 3)
-    qr_wpartial_tc_kernel(const float* __restrict__ a, float* __restrict__ Wp, int m, int n, int j0, int ncols,
-                          int ngroups, int* __restrict__ err) {
-  extern __shared__ unsigned char smem_dyn[];
-  unsigned char* base = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~(uintptr_t)1023);
-  unsigned char* Ahi = base;                  // 128 tile rows (A2 columns) x 128 B
-  unsigned char* Alo = base + 16384;
-  unsigned char* Bhi = base + 2 * 16384;      // 32 tile rows (panel columns) x 128 B
-  unsigned char* Blo = base + 2 * 16384 + 4096;
-  uint64_t* mbar = reinterpret_cast<uint64_t*>(base + 2 * 16384 + 2 * 4096);
-  uint32_t* tslot = reinterpret_cast<uint32_t*>(base + 2 * 16384 + 2 * 4096 + 16);
-  const int tid = threadIdx.x, warp = tid >> 5;
-  const int tile = blockIdx.x, grp = blockIdx.y;
-  const int cbase = j0 + kPB + tile * 128;
-  const int cw = min(128, ncols - tile * 128);
-  const int rows_total = m - j0;
-  const int per = (((rows_total + ngroups - 1) / ngroups) + kWtcRows - 1) / kWtcRows * kWtcRows;
-  const int r0 = j0 + grp * per, r1 = min(m, r0 + per);
-  if (warp == 0) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tc::smem_u32(tslot)), "r"(32));
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
-  }
-  if (tid == 0) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(tc::smem_u32(mbar)));
-    asm volatile("fence.mbarrier_init.release.cluster;");
-  }
-  asm volatile("tcgen05.fence::before_thread_sync;");
-  __syncthreads();
-  asm volatile("tcgen05.fence::after_thread_sync;");
-  const uint32_t tmem = *tslot;
-  const uint32_t a_hi = tc::smem_u32(Ahi), a_lo = tc::smem_u32(Alo), b_hi = tc::smem_u32(Bhi), b_lo = tc::smem_u32(Blo);
-  // staging map: A2 chunk = 8 row quads x 32 column quads of 4 x 4 blocks, two per thread; V chunk = 8 x 8 blocks,
-  // one per thread of the first two warps
-  const int rq = tid & 7;
-  float4 pa[2][4], pv[4];
-  auto fetch = [&](int rb) {
-#pragma unroll
-    for (int i = 0; i < 2; ++i) {
-      const int cq = (tid >> 3) + 16 * i;
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const int gr = rb + 4 * rq + j;
-        pa[i][j] = (gr < r1 && 4 * cq < cw) ? reinterpret_cast<const float4*>(a + (size_t)gr * n + cbase)[cq]
-                                            : make_float4(0.f, 0.f, 0.f, 0.f);
-      }
-    }
-    if (tid < 64) {
-      const int cq = tid >> 3;
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const int gr = rb + 4 * rq + j;
-        float4 v = gr < r1 ? reinterpret_cast<const float4*>(a + (size_t)gr * n + j0)[cq] : make_float4(0.f, 0.f, 0.f, 0.f);
-        if (rb < j0 + kPB && gr < r1) {  // rows crossing the panel's diagonal block: unit diagonal, zeros above
-          v.x = vmask<float>(v.x, gr, j0, 4 * cq);
-          v.y = vmask<float>(v.y, gr, j0, 4 * cq + 1);
-          v.z = vmask<float>(v.z, gr, j0, 4 * cq + 2);
-          v.w = vmask<float>(v.w, gr, j0, 4 * cq + 3);
-        }
-        pv[j] = v;
-      }
-    }
-  };
-  const int nchunks = r1 > r0 ? (r1 - r0 + kWtcRows - 1) / kWtcRows : 0;
-  uint32_t phase = 0;
-  // The tensor core only ever accumulates ONE 32-row chunk (12 MMAs) in TMEM; the running sum over the
-  // row group lives in fp32 registers (round-to-nearest adds).
-  float acc[32];
-#pragma unroll
-  for (int k = 0; k < 32; ++k) acc[k] = 0.f;
-  auto drain = [&]() {  // wait for the committed MMAs, add their 128 x 32 result to the register sums
-    uint32_t done = 0;
-    for (int spin = 0; spin < (1 << 22) && !done; ++spin)
-      asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}\n"
-                   : "=r"(done) : "r"(tc::smem_u32(mbar)), "r"(phase) : "memory");
-    if (!done) __trap();  // bounded wait: fail loudly, never continue with stale TMEM
-    phase ^= 1;
-    asm volatile("tcgen05.fence::after_thread_sync;");
-    uint32_t r[32];
-    const uint32_t taddr = tmem + ((uint32_t)(32 * warp) << 16);
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
-          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
-          "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
-          "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-        : "r"(taddr));
-    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-    for (int k = 0; k < 32; ++k) acc[k] += __uint_as_float(r[k]);
-    asm volatile("tcgen05.fence::before_thread_sync;");
-  };
-  if (nchunks > 0) fetch(r0);
-  for (int ch = 0; ch < nchunks; ++ch) {
-    if (ch > 0) drain();  // also frees the previous chunk's tiles and TMEM
-#pragma unroll
-    for (int i = 0; i < 2; ++i) tc::split_store_t(Ahi, Alo, 4 * ((tid >> 3) + 16 * i), rq, pa[i]);
-    if (tid < 64) tc::split_store_t(Bhi, Blo, 4 * (tid >> 3), rq, pv);
-    if (ch + 1 < nchunks) fetch(r0 + (ch + 1) * kWtcRows);  // in flight while the MMAs run
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-    __syncthreads();
-    if (tid == 0) {
-      asm volatile("tcgen05.fence::after_thread_sync;");
-#pragma unroll
-      for (int ks = 0; ks < kWtcRows / 8; ++ks) {  // K = 32 rows in steps of 8 tf32 = 32 bytes along the swizzled row
-        const uint64_t dah = tc::umma_desc(a_hi + 32 * ks), dal = tc::umma_desc(a_lo + 32 * ks);
-        const uint64_t dbh = tc::umma_desc(b_hi + 32 * ks), dbl = tc::umma_desc(b_lo + 32 * ks);
-        tc::mma_tf32_w(tmem, dal, dbh, ks > 0 ? 1u : 0u);
-        tc::mma_tf32_w(tmem, dah, dbl, 1u);
-        tc::mma_tf32_w(tmem, dah, dbh, 1u);
-      }
-      asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(tc::smem_u32(mbar)) : "memory");
-    }
-  }
-  if (nchunks > 0) drain();
-  // lane of TMEM = column of the A2 tile, TMEM column = panel column k
-  const int col = tile * 128 + tid;
-  if (tid < cw) {
-    float* out = Wp + ((size_t)grp * kPB) * ncols + col;
-#pragma unroll
-    for (int k = 0; k < 32; ++k) out[(size_t)k * ncols] = acc[k];
-  }
-  __syncthreads();
-  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(32));
-}
 
 // ------------------------------------------------------------ two-level blocking ----
 // With 32-column panels every trailing pass moves the whole trailing matrix through HBM three times for
@@ -1725,13 +1583,7 @@ int qr_large_factor(const T* A, T* a, T* taus, int m, int n, void* ws, size_t ws
   // apply the block reflector of the panel at j0 (T in Tm) to the `ncols` columns that follow it
   auto trail32 = [&](int j0, int ncols) -> int {
     const int tiles = (ncols + kUpCols - 1) / kUpCols;
-#ifdef LXB_QR_WTC_EXPERIMENT  // tcgen05 W = V^T A2: compile-time opt-in until its in-situ parity run is green
-    static const bool use_wtc = [] { const char* e = getenv("LXB_QR_WTC"); return e && atoi(e) == 1; }();
-#else
-    constexpr bool use_wtc = false;
-#endif
-    const bool w_tc = use_wtc && sizeof(T) == 4 && (n % 4 == 0) && ((reinterpret_cast<uintptr_t>(a) & 15) == 0);
-    const int wtiles = w_tc ? tiles : (ncols + kW2Tile - 1) / kW2Tile;
+    const int wtiles = (ncols + kW2Tile - 1) / kW2Tile;
     // row groups: about two waves of CTAs at the kernel's occupancy, whatever the tile count is
     const int wocc = sizeof(T) == 4 ? 4 : 2;
     int ngroups = (2 * wocc * kNumSMs + wtiles - 1) / wtiles;
@@ -1739,12 +1591,7 @@ int qr_large_factor(const T* A, T* a, T* taus, int m, int n, void* ws, size_t ws
     //  two-level blocking, <= 96 columns -- may use more row groups than wide ones)
     const int gcap = (int)std::min<size_t>(4 * kNumSMs, (size_t)kW2MaxGroups * pad4(n) / (size_t)ncols);
     ngroups = ngroups < 16 ? 16 : (ngroups > gcap ? gcap : ngroups);
-    if (w_tc) {
-      LXB_CUDA_TRY(cudaFuncSetAttribute(qr_wpartial_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kWtcSmem));
-      int* errp = reinterpret_cast<int*>(w + pl.gfull_off + kPB * kPB + kPB);
-      qr_wpartial_tc_kernel<<<dim3(wtiles, ngroups), kTcThreads, kWtcSmem, st>>>(
-          reinterpret_cast<const float*>(a), reinterpret_cast<float*>(Wp), m, n, j0, ncols, ngroups, errp);
-    } else {
+    {
       const size_t w_smem = (size_t)kW2Stages * kW2Rows * (kPB + kW2Tile) * sizeof(T);
       LXB_CUDA_TRY(cudaFuncSetAttribute(qr_wpartial_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)w_smem));
       qr_wpartial_kernel<T><<<dim3(wtiles, ngroups), kW2Threads, w_smem, st>>>(a, Wp, m, n, j0, ncols, ngroups);
@@ -1762,9 +1609,8 @@ int qr_large_factor(const T* A, T* a, T* taus, int m, int n, void* ws, size_t ws
       const int per_strip = (rblocks + strips - 1) / strips;
       strips = (rblocks + per_strip - 1) / per_strip;
       LXB_CUDA_TRY(cudaFuncSetAttribute(qr_update_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTcSmem));
-      int* errp = reinterpret_cast<int*>(w + pl.gfull_off + kPB * kPB + kPB);  // spare words after [G; w]
       qr_update_tc_kernel<<<dim3(tiles, strips), kTcThreads, kTcSmem, st>>>(
-          reinterpret_cast<float*>(a), reinterpret_cast<const float*>(W2), m, n, j0, ncols, rblocks, per_strip, errp);
+          reinterpret_cast<float*>(a), reinterpret_cast<const float*>(W2), m, n, j0, ncols, rblocks, per_strip);
     } else if ((n % V == 0) && ((reinterpret_cast<uintptr_t>(a) & 15) == 0)) {
       constexpr int RT = UpCfg<T>::RT;
       const int rblocks = (m - j0 + RT - 1) / RT;
