@@ -268,7 +268,14 @@ LXB_DECL_GMRES_DIST(f64, double)
                               int32_t flags, void* workspace, size_t workspace_bytes,               \
                               void* const* peer_buffers, int32_t world, int32_t rank,               \
                               lxb_stream_t stream);                                                 \
-  size_t lxb_cg_rowsharded_workspace_##sfx(int32_t n_local);
+  size_t lxb_cg_rowsharded_workspace_##sfx(int32_t n_local);                                        \
+  /* BiCGStab (bicgstab.py:78-205), same conventions and the same workspace / symmetric-buffer sizes */ \
+  int lxb_bicgstab_rowsharded_##sfx(const T* A_local, const T* b_local, T* x_local, int32_t* result, \
+                                    int32_t* num_steps, int32_t n, int32_t n_local,                  \
+                                    int32_t row_offset, T rtol, T atol, int32_t max_steps,           \
+                                    int32_t flags, void* workspace, size_t workspace_bytes,          \
+                                    void* const* peer_buffers, int32_t world, int32_t rank,          \
+                                    lxb_stream_t stream);
 LXB_DECL_CG_DIST(f32, float)
 LXB_DECL_CG_DIST(f64, double)
 

@@ -113,6 +113,10 @@ for _sfx, _T in (("f32", c_float), ("f64", c_double)):
          c_int32, P],
     )
     _decl(f"lxb_cg_rowsharded_workspace_{_sfx}", [c_int32], c_size_t)
+    _decl(
+        f"lxb_bicgstab_rowsharded_{_sfx}",
+        [P, P, P, P, P, c_int32, c_int32, c_int32, _T, _T, c_int32, c_int32, P, c_size_t, P, c_int32, c_int32, P],
+    )
     _decl(f"lxb_gmres_rowsharded_symm_bytes_{_sfx}", [c_int32], c_size_t)
     _decl(
         f"lxb_lsmr_rowsharded_{_sfx}",

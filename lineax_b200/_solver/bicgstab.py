@@ -26,6 +26,14 @@ class BiCGStab(AbstractLinearSolver):
             raise NotImplementedError("the native BiCGStab kernel implements the default `max_norm` test")
 
     def init(self, operator, options):
+        from .gmres import _is_row_sharded
+
+        if _is_row_sharded(operator):
+            if operator.rows != operator.cols:
+                raise ValueError(
+                    "`BiCGstab(..., normal=False)` may only be used for linear solves with square matrices."
+                )
+            return operator
         if not tr.structure_equal(operator.in_structure(), operator.out_structure()):
             raise ValueError(
                 "`BiCGstab(..., normal=False)` may only be used for linear solves with square matrices."
@@ -34,6 +42,22 @@ class BiCGStab(AbstractLinearSolver):
 
     def compute(self, state, vector, options):
         operator = state
+        from .gmres import _is_row_sharded
+
+        if _is_row_sharded(operator):
+            from ..distributed import RowShardedBiCGStab
+
+            if options.get("preconditioner") is not None:
+                raise NotImplementedError("row-sharded BiCGStab takes no preconditioner")
+            x64 = config.enable_x64
+            if x64 is None:
+                x64 = operator.local.dtype == torch.float64
+            key = (operator.rows, float(self.rtol), float(self.atol), self.max_steps, bool(x64), operator.local.dtype)
+            solver = operator.sharded_solver("bicgstab", key, lambda: RowShardedBiCGStab(
+                operator.rows, float(self.rtol), float(self.atol), max_steps=self.max_steps, x64=x64,
+                dtype=operator.local.dtype, group=operator.group))
+            x, result, steps = solver.solve(operator.local, vector, options.get("y0"))
+            return x, result, {"num_steps": steps, "max_steps": self.max_steps}
         a, b, m, y0, size, _ = flat_problem(operator, vector, options)
         ms, flags = steps_flags(self.max_steps, size)
         x64 = config.enable_x64

@@ -124,13 +124,145 @@ __global__ void __launch_bounds__(kDistThreads) cg_dist_kernel(CgDistParams<T> d
   team.finish(sc);
 }
 
+// Row-sharded BiCGStab (lineax/_solver/bicgstab.py:78-205, no preconditioner): same decomposition; per
+// iteration two all-gathers (p and s, each fused with the exchange round that also makes it a barrier)
+// and four all-reduce rounds (rho', <r0, v>, {<s, t>, <t, t>}, the two max-norms of the convergence test).
 template <typename T>
-size_t cg_dist_ws_bytes(int n_local) { return (grid_part_elems() + 5 * pad4(n_local)) * sizeof(T); }
+__global__ void __launch_bounds__(kDistThreads) bicgstab_dist_kernel(CgDistParams<T> dp) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const KrylovParams<T>& p = dp.k;
+  const int n = dp.n_global, nl = p.n, off = dp.row_offset;
+  T* red = reinterpret_cast<T*>(smem_raw);
+  T* sc = red + 96 + kGridMaxK;
+  T* xs = dp.stage_x ? reinterpret_cast<T*>((reinterpret_cast<uintptr_t>(sc + 8) + 15) & ~(uintptr_t)15) : nullptr;
+  const size_t lpad = ((size_t)nl + 3) & ~(size_t)3;
+  T* part = p.ws;
+  DistTeam<T> team(part, red, dp.peers, dp.world, dp.rank);
+  GridTeam<T>& g = team.g;
+  T* wy = part + grid_part_elems();
+  T* wr0 = wy + lpad;
+  T* wr = wr0 + lpad;
+  T* wp = wr + lpad;
+  T* wv = wp + lpad;
+  T* wss = wv + lpad;
+  T* wt = wss + lpad;
+  T* wd = wt + lpad;
+  int lo, hi;
+  g.slice(nl, lo, hi);
+  const int tid = g.tid, nt = g.nt;
+  const bool has_scale = !(p.rtol == T(0) && p.atol == T(0));
+  const bool x64 = (p.flags & LXB_X64_BREAKDOWN) != 0;
+  const T* A = p.A;
+  const T* b = p.b;
+  T* xfull = team.xchg();
+  auto gather_matvec = [&](const T* v, T* out) {
+    team.push(v, lo, hi, off);
+    team.xround(sc, 0, sc, 0);
+    grid_matvec<T>(A, n, lo, hi, xfull, out, T(1), xs);
+  };
+  auto xdot = [&](const T* a, const T* c) -> T {
+    T v[1] = {T(0)};
+    for (int i = lo + tid; i < hi; i += nt) v[0] = fma_(a[i], c[i], v[0]);
+    block_sum<T, 1>(v, red);
+    if (tid == 0) sc[0] = v[0];
+    team.xround(sc, 1, sc, 0);
+    const T r = sc[0];
+    __syncthreads();
+    return r;
+  };
+  auto breakdown = [&](T omega, T alpha, T rho) -> bool {
+    if (x64) return omega == T(0) || alpha == T(0) || rho == T(0);
+    const T t = T(1e-16);
+    return omega < t || alpha < t || rho < t;  // signed test, bicgstab.py:110-113
+  };
+  // convergence test of bicgstab.py:115-126 over all GPUs
+  auto not_converged = [&](bool diff_inf) -> bool {
+    if (!has_scale) return true;
+    T v[2] = {T(0), T(0)};
+    for (int i = lo + tid; i < hi; i += nt) {
+      const T d = diff_inf ? Num<T>::inf() : wd[i];
+      v[0] = absmax2(v[0], wr[i] / (p.atol + p.rtol * abs_(b[i])));
+      v[1] = absmax2(v[1], d / (p.atol + p.rtol * abs_(wy[i])));
+    }
+    block_absmax<T, 2>(v, red);
+    if (tid == 0) { sc[1] = v[0]; sc[2] = v[1]; }
+    team.xround(sc, 0, sc + 1, 2);
+    const bool nc = (sc[1] > T(1)) || (sc[2] > T(1));
+    __syncthreads();
+    return nc;
+  };
+
+  for (int i = lo + tid; i < hi; i += nt) {
+    wy[i] = (p.flags & LXB_HAS_Y0) ? p.x[i] : T(0);
+    wp[i] = T(0);
+    wv[i] = T(0);
+  }
+  __syncthreads();
+  gather_matvec(wy, wt);
+  for (int i = lo + tid; i < hi; i += nt) {
+    const T r = b[i] - wt[i];
+    wr0[i] = r;
+    wr[i] = r;
+  }
+  __syncthreads();
+  T alpha = T(1), omega = T(1), rho = T(1);
+  int64_t step = 0;
+  bool diff_inf = true;
+  while (true) {
+    if (breakdown(omega, alpha, rho)) break;
+    if (!not_converged(diff_inf)) break;
+    if (!(step < p.max_steps)) break;
+    const T rho_new = xdot(wr0, wr);
+    const T beta = (rho_new / rho) * (alpha / omega);
+    for (int i = lo + tid; i < hi; i += nt) wp[i] = wr[i] + beta * (wp[i] - omega * wv[i]);
+    __syncthreads();
+    gather_matvec(wp, wv);
+    alpha = rho_new / xdot(wr0, wv);
+    for (int i = lo + tid; i < hi; i += nt) wss[i] = wr[i] - alpha * wv[i];
+    __syncthreads();
+    gather_matvec(wss, wt);
+    {
+      T d2[2] = {T(0), T(0)};
+      for (int i = lo + tid; i < hi; i += nt) {
+        d2[0] = fma_(wss[i], wt[i], d2[0]);
+        d2[1] = fma_(wt[i], wt[i], d2[1]);
+      }
+      block_sum<T, 2>(d2, red);
+      if (tid == 0) { sc[0] = d2[0]; sc[1] = d2[1]; }
+      team.xround(sc, 2, sc, 0);
+      omega = sc[0] / sc[1];
+      __syncthreads();
+    }
+    for (int i = lo + tid; i < hi; i += nt) {
+      const T d = alpha * wp[i] + omega * wss[i];
+      wd[i] = d;
+      wy[i] = wy[i] + d;
+      wr[i] = wss[i] - omega * wt[i];
+    }
+    diff_inf = false;
+    rho = rho_new;
+    step += 1;
+    __syncthreads();
+  }
+  int result = krylov_final_result(step, p.max_steps, p.flags, has_scale);
+  const bool nc = not_converged(diff_inf);
+  if (breakdown(omega, alpha, rho) && nc) result = LXB_BREAKDOWN;
+  for (int i = lo + tid; i < hi; i += nt) p.x[i] = wy[i];
+  if (g.bid == 0 && tid == 0) {
+    p.result[0] = result;
+    p.num_steps[0] = (int32_t)step;
+  }
+  team.finish(sc);
+}
+
+template <typename T>
+size_t cg_dist_ws_bytes(int n_local) { return (grid_part_elems() + 8 * pad4(n_local)) * sizeof(T); }  // BiCGStab: 8 vectors
 
 template <typename T>
 int cg_dist_launch(const T* A_local, const T* b_local, T* x_local, int32_t* result, int32_t* num_steps, int n,
                    int n_local, int row_offset, T rtol, T atol, int max_steps, int stabilise_every, int flags,
-                   void* ws, size_t ws_bytes, void* const* peers, int world, int rank, cudaStream_t st) {
+                   void* ws, size_t ws_bytes, void* const* peers, int world, int rank, cudaStream_t st,
+                   bool bicgstab = false) {
   if (!A_local || !b_local || !x_local || !result || !num_steps || !peers || n <= 0 || n_local < 0 ||
       world < 1 || world > kMaxPeers || rank < 0 || rank >= world)
     return LXB_E_BADARG;
@@ -146,7 +278,7 @@ int cg_dist_launch(const T* A_local, const T* b_local, T* x_local, int32_t* resu
   const size_t xbytes = pad4(n) * sizeof(T);
   dp.stage_x = smem + xbytes <= 200 * 1024;
   if (dp.stage_x) smem += xbytes;
-  auto kern = cg_dist_kernel<T>;
+  auto kern = bicgstab ? bicgstab_dist_kernel<T> : cg_dist_kernel<T>;
   LXB_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int occ = 0, dev = 0, sms = 0;
   LXB_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kDistThreads, smem));
@@ -178,6 +310,17 @@ int cg_dist_launch(const T* A_local, const T* b_local, T* x_local, int32_t* resu
   }                                                                                                  \
   extern "C" size_t lxb_cg_rowsharded_workspace_##sfx(int32_t n_local) {                             \
     return lxb::cg_dist_ws_bytes<T>(n_local);                                                        \
+  }                                                                                                  \
+  extern "C" int lxb_bicgstab_rowsharded_##sfx(const T* A_local, const T* b_local, T* x_local,       \
+                                               int32_t* result, int32_t* num_steps, int32_t n,       \
+                                               int32_t n_local, int32_t row_offset, T rtol, T atol,  \
+                                               int32_t max_steps, int32_t flags, void* workspace,    \
+                                               size_t workspace_bytes, void* const* peer_buffers,    \
+                                               int32_t world, int32_t rank, lxb_stream_t stream) {   \
+    return lxb::cg_dist_launch<T>(A_local, b_local, x_local, result, num_steps, n, n_local,          \
+                                  row_offset, rtol, atol, max_steps, 0, flags, workspace,            \
+                                  workspace_bytes, peer_buffers, world, rank, (cudaStream_t)stream,  \
+                                  true);                                                             \
   }
 LXB_DEF_CG_DIST(f32, float)
 LXB_DEF_CG_DIST(f64, double)

@@ -109,6 +109,38 @@ class RowShardedCG(RowShardedGMRES):
         return x, result[0], steps[0]
 
 
+class RowShardedBiCGStab(RowShardedGMRES):
+    """BiCGStab (lineax/_solver/bicgstab.py semantics, no preconditioner) on a row-partitioned operator."""
+
+    def __init__(self, n: int, rtol: float, atol: float, *, max_steps=None, x64=None, dtype=torch.float32, group=None):
+        super().__init__(n, rtol, atol, max_steps=max_steps, dtype=dtype, group=group)
+        self.x64 = (dtype == torch.float64) if x64 is None else bool(x64)
+
+    def solve(self, a_local: torch.Tensor, b_local: torch.Tensor, y0_local: torch.Tensor | None = None):
+        lo, hi = self.row_range()
+        nl = hi - lo
+        if tuple(a_local.shape) != (nl, self.n) or tuple(b_local.shape) != (nl,):
+            raise ValueError(f"rank {self.rank}: expected A_local {(nl, self.n)} and b_local {(nl,)}")
+        a_local = a_local.to(self.dtype).contiguous()
+        b_local = b_local.to(self.dtype).contiguous()
+        flags = (0 if self.max_steps is None else nat.MAXSTEPS_GIVEN) | (nat.X64_BREAKDOWN if self.x64 else 0)
+        ms = 10 * self.n if self.max_steps is None else int(self.max_steps)
+        if y0_local is not None:
+            x = y0_local.to(self.dtype).contiguous().clone()
+            flags |= nat.HAS_Y0
+        else:
+            x = torch.empty(nl, dtype=self.dtype, device=self.device)
+        result = torch.empty(1, dtype=torch.int32, device=self.device)
+        steps = torch.empty(1, dtype=torch.int32, device=self.device)
+        ws_bytes = nat.fn(f"lxb_cg_rowsharded_workspace_{self.sfx}")(nl)
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=self.device)
+        nat.call(f"lxb_bicgstab_rowsharded_{self.sfx}", a_local.data_ptr(), b_local.data_ptr(), x.data_ptr(),
+                 result.data_ptr(), steps.data_ptr(), self.n, nl, lo, self.rtol, self.atol, ms, flags,
+                 ws.data_ptr(), ws_bytes, self.peers_dev, self.world, self.rank,
+                 torch.cuda.current_stream().cuda_stream)
+        return x, result[0], steps[0]
+
+
 class RowShardedLSMR:
     """LSMR (lineax/_solver/lsmr.py semantics) on a tall dense operator partitioned by ROWS.
 
