@@ -731,10 +731,10 @@ __device__ __forceinline__ int sw128(int r, int c) { return (r >> 3) * 1024 + (r
 // ignores the 13 low mantissa bits of an fp32 operand) biases every product towards zero by ~2^-22, and
 // over a 262144-row contraction that bias does not average out (measured: ||R - R64||_F / ||R64||_F grew
 // linearly with n, 2.5e-6 at n = 2048, against 1e-7 with rounding).
+// cvt.rna.tf32.f32 is emulated on sm_100a (FSETP + VIADD + LOP3 + SEL per value: it was most of the staging
+// instructions); round-to-nearest, ties away, on the magnitude bits is an add and a mask.
 __device__ __forceinline__ float tf32_rn(float x) {
-  uint32_t r;
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
-  return __uint_as_float(r);
+  return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xffffe000u);
 }
 __device__ __forceinline__ void split_store(unsigned char* hi, unsigned char* lo, int r, int c, float4 x) {
   float4 h, l;
@@ -1320,6 +1320,264 @@ __global__ void __launch_bounds__(kTcThreads, 2)
   if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(256));
 }
 
+// Warp-specialised version of the K = 128 update (default; LXB_QR_UP2=0 selects qr_update128_tc_kernel).
+// ncu showed the kernel above latency bound (long_scoreboard 52 %, tensor pipe 16 %): every thread stages,
+// waits for the MMAs and writes back in turn, and the hi/lo split of the SAME V block is redone by every
+// 64-column tile (12 of every 14 executed instructions).  So
+//   qr_vsplit_kernel  splits V ONCE per outer block into the exact shared-memory operand images
+//                     (swizzled 128 x 32 tiles, hi then lo: 32 KB per K-chunk) in the workspace, and
+//   qr_update128_ws_kernel runs three jobs concurrently in one persistent CTA per SM:
+//     warp 5     PRODUCER: one thread copies a chunk's 32 KB image global -> shared with cp.async.bulk
+//                (mbarrier complete_tx) into a 4-stage ring; the other lanes prefetch A2 tiles into L2
+//     warp 4     one thread issues the 12 tcgen05.mma of a chunk as soon as its stage is full, commits the
+//                stage back to the producer and, after the 4th chunk, the accumulator to the epilogue
+//     warps 0-3  EPILOGUE: A2 tile loaded BEFORE the accumulator is waited for, TMEM -> registers, turned
+//                around in shared memory, subtracted and stored; two TMEM accumulators (2 x 64 columns)
+//                let the MMAs of row block b + 1 run under the epilogue of block b.
+// All waits are mbarrier waits with a bounded spin that traps (no hang on a protocol error).
+constexpr int kU2Threads = 192;
+constexpr int kU2Stages = 4;
+constexpr size_t kU2Smem = 8 * 8192 + kU2Stages * 2 * 16384 + 8 * 4096 + 1024 + 128;
+constexpr size_t kVimgBlockFloats = 4 * 2 * 4096;  // one 128-row block: 4 K-chunks x {hi, lo} x 16 KB
+
+namespace tc {
+__device__ __forceinline__ void mbar_init(uint64_t* b, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(b)), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* b) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(b)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait_parity(uint64_t* b, uint32_t parity) {
+  uint32_t done = 0;
+  for (int spin = 0; spin < (1 << 22) && !done; ++spin)
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}\n"
+                 : "=r"(done) : "r"(smem_u32(b)), "r"(parity) : "memory");
+  if (!done) __trap();
+}
+__device__ __forceinline__ void umma_commit(uint64_t* b) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(b)) : "memory");
+}
+__device__ __forceinline__ void sts128(uint32_t addr, float4 v) {
+  asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+__device__ __forceinline__ float4 lds128(uint32_t addr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr) : "memory");
+  return v;
+}
+__device__ __forceinline__ float4 ldg128(const float* p) {
+  float4 v;
+  asm volatile("ld.global.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void stg128(float* p, float4 v) {
+  asm volatile("st.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+// split_store with shared-window addresses (STS, not generic ST)
+__device__ __forceinline__ void split_sts(uint32_t hi, uint32_t lo, int r, int c, float4 x) {
+  float4 h, l;
+  h.x = tf32_rn(x.x); l.x = tf32_rn(x.x - h.x);
+  h.y = tf32_rn(x.y); l.y = tf32_rn(x.y - h.y);
+  h.z = tf32_rn(x.z); l.z = tf32_rn(x.z - h.z);
+  h.w = tf32_rn(x.w); l.w = tf32_rn(x.w - h.w);
+  sts128(hi + sw128(r, c), h);
+  sts128(lo + sw128(r, c), l);
+}
+}  // namespace tc
+
+// V (columns j0 .. j0+127, rows j0 .., unit diagonal / zeros above applied) -> operand images.
+// grid (4 K-chunks, row blocks), 256 threads: thread = (row r0 + 32 i, 16-byte chunk q).
+__global__ void __launch_bounds__(256) qr_vsplit_kernel(const float* __restrict__ a, float* __restrict__ vimg, int m, int n,
+                                                        int j0) {
+  const int kc = blockIdx.x, b = blockIdx.y, q = threadIdx.x & 7, r0 = threadIdx.x >> 3;
+  unsigned char* hi = reinterpret_cast<unsigned char*>(vimg + (size_t)b * kVimgBlockFloats + (size_t)kc * 8192);
+  unsigned char* lo = hi + 16384;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int r = r0 + 32 * i, gr = j0 + b * 128 + r;
+    float4 v = gr < m ? *reinterpret_cast<const float4*>(a + (size_t)gr * n + j0 + 32 * kc + 4 * q) : make_float4(0.f, 0.f, 0.f, 0.f);
+    if (b == 0) {
+      v.x = vmask<float>(v.x, gr, j0, 32 * kc + 4 * q);
+      v.y = vmask<float>(v.y, gr, j0, 32 * kc + 4 * q + 1);
+      v.z = vmask<float>(v.z, gr, j0, 32 * kc + 4 * q + 2);
+      v.w = vmask<float>(v.w, gr, j0, 32 * kc + 4 * q + 3);
+    }
+    tc::split_store(hi, lo, r, q, v);
+  }
+}
+
+__global__ void __launch_bounds__(kU2Threads, 1)
+    qr_update128_ws_kernel(float* __restrict__ a, const float* __restrict__ Yt, const float* __restrict__ vimg, int m, int n,
+                           int j0, int ncols, int rblocks, int ntiles, int gsz) {
+  extern __shared__ unsigned char smem_dyn[];
+  const uint32_t sbase = (tc::smem_u32(smem_dyn) + 1023u) & ~1023u;  // shared-window addresses throughout
+  const uint32_t Bt = sbase;                                  // 4 K-chunks x {hi, lo} x (64 columns x 128 B)
+  const uint32_t ring = sbase + 8 * 8192;                     // kU2Stages x {hi 16 KB, lo 16 KB}
+  const uint32_t epi = ring + kU2Stages * 2 * 16384;          // 4 warps x 2 halves x 4 KB
+  unsigned char* gbase = smem_dyn + (sbase - tc::smem_u32(smem_dyn));
+  uint64_t* full = reinterpret_cast<uint64_t*>(gbase + 8 * 8192 + kU2Stages * 2 * 16384 + 8 * 4096);
+  uint64_t* empty = full + kU2Stages;
+  uint64_t* accf = empty + kU2Stages;
+  uint64_t* acce = accf + 2;
+  uint32_t* tslot = reinterpret_cast<uint32_t*>(acce + 2);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  // Work items = (group of `gsz` row blocks, tile), group-major and dealt round-robin: at any moment the
+  // CTAs are on the same few row groups, so the V images and A2 rows they share are found in L2.
+  const int ngroups = (rblocks + gsz - 1) / gsz;
+  const int nitems = ngroups * ntiles;
+  if ((int)blockIdx.x >= nitems) return;  // uniform per CTA
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tc::smem_u32(tslot)), "r"(128));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  if (tid == 0) {
+    for (int s2 = 0; s2 < kU2Stages; ++s2) {
+      tc::mbar_init(full + s2, 1);
+      tc::mbar_init(empty + s2, 1);
+    }
+    for (int q = 0; q < 2; ++q) {
+      tc::mbar_init(accf + q, 1);
+      tc::mbar_init(acce + q, 128);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;");
+  const uint32_t tmem = *tslot;
+  int chunk_ctr = 0;  // chunks this CTA has pushed through the ring (same count in producer and issuer)
+  int blk_ctr = 0;    // row blocks this CTA has accumulated (same count in issuer and epilogue)
+
+  for (int item = blockIdx.x; item < nitems; item += gridDim.x) {
+    const int tile = item % ntiles, b0 = (item / ntiles) * gsz;
+    const int b1 = min(rblocks, b0 + gsz);
+    const int nblk = b1 - b0;
+    const int cbase = j0 + kOB + tile * 64;
+    const int cw = min(64, ncols - tile * 64);
+    // Y tile (all threads): tile row = column of A2 (N index), 128 B of K per chunk.  The previous
+    // item's MMAs are complete (its epilogue waited for the last accumulator before the barrier below).
+    for (int idx = tid; idx < 2048; idx += kU2Threads) {
+      const int q = idx & 7, c = (idx >> 3) & 63, kc = idx >> 9;
+      const float4 y = c < cw ? tc::ldg128(Yt + (size_t)(tile * 64 + c) * kOB + 32 * kc + 4 * q)
+                              : make_float4(0.f, 0.f, 0.f, 0.f);
+      tc::split_sts(Bt + (2 * kc) * 8192, Bt + (2 * kc + 1) * 8192, c, q, y);
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    __syncthreads();
+
+    if (warp == 5) {
+      // ---------------- producer: bulk copies of the pre-split V images ----------------
+      auto prefetch_tile = [&](int bb) {  // a later row block's A2 tile into L2 (the epilogue reads it)
+        if (bb < b1) {
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const int gr = j0 + bb * 128 + lane + 32 * i;
+            if (gr < m) {
+              const float* row = a + (size_t)gr * n + cbase;
+              asm volatile("prefetch.global.L2 [%0];" ::"l"(row));
+              if (cw > 32) asm volatile("prefetch.global.L2 [%0];" ::"l"(row + 32));
+            }
+          }
+        }
+      };
+      prefetch_tile(b0 + 1);
+      prefetch_tile(b0 + 2);
+      for (int c = 0; c < nblk * 4; ++c) {
+        if (lane == 0) {
+          const int cc = chunk_ctr + c, st = cc % kU2Stages, use = cc / kU2Stages;
+          if (use > 0) tc::mbar_wait_parity(empty + st, (uint32_t)((use - 1) & 1));  // MMAs of the previous use done
+          const float* src = vimg + (size_t)(b0 + c / 4) * kVimgBlockFloats + (size_t)(c & 3) * 8192;
+          const uint32_t mb = tc::smem_u32(full + st);
+          asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mb), "r"(32768) : "memory");
+          asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                           ring + st * 32768),
+                       "l"(src), "r"(32768), "r"(mb)
+                       : "memory");
+        }
+        if ((c & 3) == 0) prefetch_tile(b0 + c / 4 + 3);
+        __syncwarp();
+      }
+    } else if (warp == 4) {
+      // ---------------- MMA issuer ----------------
+      if (lane == 0) {
+        for (int c = 0; c < nblk * 4; ++c) {
+          const int cc = chunk_ctr + c, st = cc % kU2Stages, use = cc / kU2Stages;
+          const int kc = c & 3, bc = blk_ctr + c / 4, buf = bc & 1, ub = bc >> 1;
+          if (kc == 0 && ub > 0) tc::mbar_wait_parity(acce + buf, (uint32_t)((ub - 1) & 1));  // accumulator drained
+          tc::mbar_wait_parity(full + st, (uint32_t)(use & 1));
+          asm volatile("tcgen05.fence::after_thread_sync;");
+          const uint32_t a_hi = ring + st * 2 * 16384, a_lo = a_hi + 16384;
+          const uint32_t b_hi = Bt + (2 * kc) * 8192, b_lo = Bt + (2 * kc + 1) * 8192;
+#pragma unroll
+          for (int ks = 0; ks < 4; ++ks) {
+            const uint64_t dah = tc::umma_desc(a_hi + 32 * ks), dal = tc::umma_desc(a_lo + 32 * ks);
+            const uint64_t dbh = tc::umma_desc(b_hi + 32 * ks), dbl = tc::umma_desc(b_lo + 32 * ks);
+            tc::mma_tf32_n64(tmem + 64 * buf, dal, dbh, (kc > 0 || ks > 0) ? 1u : 0u);
+            tc::mma_tf32_n64(tmem + 64 * buf, dah, dbl, 1u);
+            tc::mma_tf32_n64(tmem + 64 * buf, dah, dbh, 1u);
+          }
+          tc::umma_commit(empty + st);               // stage free once these MMAs have read it
+          if (kc == 3) tc::umma_commit(accf + buf);  // accumulator complete
+        }
+      }
+    } else if (warp < 4) {
+      // ---------------- epilogue (warps 0-3 = TMEM lane quarters 0-3) ----------------
+      const uint32_t S0 = epi + warp * 8192, S1 = S0 + 4096;
+      const int c = lane & 7, lr = lane >> 3;
+      auto load_x = [&](int rb, int qc, float4 (&x)[8]) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int gr = rb + 32 * warp + 4 * i + lr, col = 32 * qc + 4 * c;
+          if (gr < m && col < cw) x[i] = tc::ldg128(a + (size_t)gr * n + cbase + col);
+        }
+      };
+      auto to_smem = [&](uint32_t S, uint32_t taddr) {  // thread = row of the tile; written so reads are row-major
+        uint32_t r[32];
+        tc::tmem_ld32(taddr, r);
+#pragma unroll
+        for (int g4 = 0; g4 < 8; ++g4)
+          tc::sts128(S + 16 * (lane * 8 + (g4 ^ (lane & 7))),
+                     make_float4(__uint_as_float(r[4 * g4]), __uint_as_float(r[4 * g4 + 1]), __uint_as_float(r[4 * g4 + 2]),
+                                 __uint_as_float(r[4 * g4 + 3])));
+      };
+      auto finish = [&](uint32_t S, int rb, int qc, const float4 (&x)[8]) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int rr = 4 * i + lr, gr = rb + 32 * warp + rr, col = 32 * qc + 4 * c;
+          if (gr < m && col < cw) {
+            const float4 p = tc::lds128(S + 16 * (rr * 8 + (c ^ (rr & 7))));
+            float4 y = x[i];
+            y.x -= p.x; y.y -= p.y; y.z -= p.z; y.w -= p.w;
+            tc::stg128(a + (size_t)gr * n + cbase + col, y);
+          }
+        }
+      };
+      for (int blk = 0; blk < nblk; ++blk) {
+        const int rb = j0 + (b0 + blk) * 128, bc = blk_ctr + blk, buf = bc & 1, ub = bc >> 1;
+        float4 x0[8], x1[8];
+        load_x(rb, 0, x0);  // in flight while the accumulator is waited for
+        load_x(rb, 1, x1);
+        tc::mbar_wait_parity(accf + buf, (uint32_t)(ub & 1));
+        asm volatile("tcgen05.fence::after_thread_sync;");
+        __syncwarp();  // the previous block's reads of S0/S1 are done
+        to_smem(S0, tmem + ((uint32_t)(32 * warp) << 16) + 64 * buf);
+        to_smem(S1, tmem + ((uint32_t)(32 * warp) << 16) + 64 * buf + 32);
+        asm volatile("tcgen05.fence::before_thread_sync;");
+        tc::mbar_arrive(acce + buf);  // the MMAs of the block after next may overwrite this accumulator
+        __syncwarp();
+        finish(S0, rb, 0, x0);
+        finish(S1, rb, 1, x1);
+      }
+    }
+    chunk_ctr += nblk * 4;
+    blk_ctr += nblk;
+    __syncthreads();  // item done: every MMA that reads the Y tile has completed (epilogue saw the last accumulator)
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;");
+  __syncthreads();
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(128));
+}
+
 // --------------------------------------------------- apply Q^T to one vector ----
 // y <- H_n ... H_2 H_1 y, one 32-reflector block at a time with TWO grid barriers per block
 // (instead of one per reflector).  For block V (unit lower trapezoidal, taus t):
@@ -1516,7 +1774,7 @@ __global__ void __launch_bounds__(1024) qr_rsolve_kernel(const T* __restrict__ a
 template <typename T>
 struct QrLargePlan {
   int nb, nb_panel, rows_cta;
-  size_t smem_panel, ws_bytes, wp_off, w2_off, t_off, gpart_off, gfull_off, y_off, tbig_off, yt_off;
+  size_t smem_panel, ws_bytes, wp_off, w2_off, t_off, gpart_off, gfull_off, y_off, tbig_off, yt_off, vimg_off;
   int ngroups, in_smem;
   bool ok;
 };
@@ -1546,6 +1804,9 @@ QrLargePlan<T> qr_large_plan(int m, int n) {
   pl.y_off = off; off += pad4(m);
   pl.tbig_off = off; off += (size_t)kOB * kOB;        // T of an outer block (two-level blocking)
   pl.yt_off = off; off += (size_t)kOB * pad4(n);      // Y = T^T W, transposed
+  off = (off + 255) & ~(size_t)255;
+  pl.vimg_off = off;                                  // pre-split operand images of an outer block's V
+  if (sizeof(T) == 4 && n > kOB) off += (size_t)((m + 127) / 128) * kVimgBlockFloats;
   pl.ws_bytes = off * sizeof(T);
   pl.ok = true;
   return pl;
@@ -1660,6 +1921,7 @@ int qr_large_factor(const T* A, T* a, T* taus, int m, int n, void* ws, size_t ws
     LXB_CUDA_TRY(cudaFuncSetAttribute(qr_wbig_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kWbigSmem));
     LXB_CUDA_TRY(cudaFuncSetAttribute(qr_wbig_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kWbigSmem));
     LXB_CUDA_TRY(cudaFuncSetAttribute(qr_update128_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kUp128Smem));
+    LXB_CUDA_TRY(cudaFuncSetAttribute(qr_update128_ws_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kU2Smem));
     const size_t tb_smem = (size_t)2 * kOB * (kOB + 1) * sizeof(float);
     LXB_CUDA_TRY(cudaFuncSetAttribute(qr_tbig_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tb_smem));
     const size_t wp_cap = (size_t)pl.ngroups * kPB * pad4(n);  // elements reserved for row-group partials
@@ -1701,7 +1963,22 @@ int qr_large_factor(const T* A, T* a, T* taus, int m, int n, void* ws, size_t ws
       strips = strips < 1 ? 1 : (strips > rblocks ? rblocks : strips);
       const int per_strip = (rblocks + strips - 1) / strips;
       strips = (rblocks + per_strip - 1) / per_strip;
-      qr_update128_tc_kernel<<<dim3(ut, strips), kTcThreads, kUp128Smem, st>>>(af, Yt, m, n, j0, ncols, rblocks, per_strip);
+      static const bool up2 = [] { const char* e = getenv("LXB_QR_UP2"); return !(e && atoi(e) == 0); }();
+      if (up2) {
+        // one persistent CTA per SM; groups of <= 32 row blocks, sized for about a whole number of rounds
+        const int64_t cells = (int64_t)ut * rblocks;
+        const int rounds = (int)((cells + (int64_t)kNumSMs * 32 - 1) / ((int64_t)kNumSMs * 32));
+        int gsz = (int)((cells + (int64_t)kNumSMs * rounds - 1) / ((int64_t)kNumSMs * rounds));
+        gsz = gsz < 1 ? 1 : (gsz > rblocks ? rblocks : gsz);
+        const int64_t nitems = (int64_t)((rblocks + gsz - 1) / gsz) * ut;
+        const int g2 = (int)(nitems < kNumSMs ? nitems : kNumSMs);
+        float* vimg = reinterpret_cast<float*>(w + pl.vimg_off);
+        qr_vsplit_kernel<<<dim3(4, rblocks), 256, 0, st>>>(af, vimg, m, n, j0);
+        LXB_CUDA_CHECK_LAUNCH();
+        qr_update128_ws_kernel<<<g2, kU2Threads, kU2Smem, st>>>(af, Yt, vimg, m, n, j0, ncols, rblocks, ut, gsz);
+      } else {
+        qr_update128_tc_kernel<<<dim3(ut, strips), kTcThreads, kUp128Smem, st>>>(af, Yt, m, n, j0, ncols, rblocks, per_strip);
+      }
       LXB_CUDA_CHECK_LAUNCH();
     }
   }

@@ -1,9 +1,10 @@
 #!/bin/bash
-set -x
+# QR two-level path: accuracy vs float64, the QR parity tests, and the qr262k bench line.
 mkdir -p gpurun_out
-timeout 900 python -m pytest tests/test_direct_gpu.py -q -m gpu -k "qr" -x > gpurun_out/r02_pytest_qr.log 2>&1; tail -15 gpurun_out/r02_pytest_qr.log
-for v in LXB_QR_TWOLEVEL=1 LXB_QR_TWOLEVEL=0; do
-  env $v timeout 600 python bench.py --workload qr262k --no-cpu-baseline > gpurun_out/r02_bench_qr_$v.json 2> gpurun_out/r02_bench_qr_$v.err
-  python -c "import json; d=json.load(open('gpurun_out/r02_bench_qr_$v.json')); print('RESULT $v', d['ms_per_step'], d['roofline']['frac'], d['parity'])" || tail -5 gpurun_out/r02_bench_qr_$v.err
-done
-timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/r02_launches_qr262k.csv python bench.py --workload qr262k --steps 3 --warmup 3 --no-cpu-baseline > gpurun_out/r02_ncu_qr.log 2>&1
+{
+  timeout 120 python tools/qr_tc_accuracy.py 32768 1024
+  timeout 120 python tools/qr_tc_accuracy.py 20000 1100
+  timeout 200 python bench.py --workload qr262k --no-cpu-baseline --steps 5 --warmup 3
+  timeout 300 python -m pytest tests/test_direct_gpu.py tests/test_fullsize_gpu.py -m gpu -x -q -k "qr or QR" 2>&1 | tail -5
+} > gpurun_out/qr_probe.log 2>&1
+grep -v '^{' gpurun_out/qr_probe.log | tail; grep -o '"ms_per_step": [0-9.]*' gpurun_out/qr_probe.log
