@@ -1336,7 +1336,7 @@ __global__ void __launch_bounds__(kTcThreads, 2)
 //                let the MMAs of row block b + 1 run under the epilogue of block b.
 // All waits are mbarrier waits with a bounded spin that traps (no hang on a protocol error).
 constexpr int kU2Threads = 192;
-constexpr int kU2Stages = 4;
+constexpr int kU2Stages = 4;  // == K-chunks per row block: chunk kc always uses stage kc
 constexpr size_t kU2Smem = 8 * 8192 + kU2Stages * 2 * 16384 + 8 * 4096 + 1024 + 128;
 constexpr size_t kVimgBlockFloats = 4 * 2 * 4096;  // one 128-row block: 4 K-chunks x {hi, lo} x 16 KB
 
@@ -1353,6 +1353,11 @@ __device__ __forceinline__ void mbar_wait_parity(uint64_t* b, uint32_t parity) {
     asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}\n"
                  : "=r"(done) : "r"(smem_u32(b)), "r"(parity) : "memory");
   if (!done) __trap();
+}
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}\n" : "=r"(pred));
+  return pred != 0;
 }
 __device__ __forceinline__ void umma_commit(uint64_t* b) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(b)) : "memory");
@@ -1445,8 +1450,7 @@ __global__ void __launch_bounds__(kU2Threads, 1)
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;");
   const uint32_t tmem = *tslot;
-  int chunk_ctr = 0;  // chunks this CTA has pushed through the ring (same count in producer and issuer)
-  int blk_ctr = 0;    // row blocks this CTA has accumulated (same count in issuer and epilogue)
+  int blk_ctr = 0;    // row blocks this CTA has accumulated (same count in producer, issuer and epilogue)
 
   for (int item = blockIdx.x; item < nitems; item += gridDim.x) {
     const int tile = item % ntiles, b0 = (item / ntiles) * gsz;
@@ -1482,42 +1486,51 @@ __global__ void __launch_bounds__(kU2Threads, 1)
       };
       prefetch_tile(b0 + 1);
       prefetch_tile(b0 + 2);
-      for (int c = 0; c < nblk * 4; ++c) {
+      // 4 chunks per row block and a 4-stage ring: chunk kc always lands in stage kc, use = row-block count
+      for (int blk = 0; blk < nblk; ++blk) {
         if (lane == 0) {
-          const int cc = chunk_ctr + c, st = cc % kU2Stages, use = cc / kU2Stages;
-          if (use > 0) tc::mbar_wait_parity(empty + st, (uint32_t)((use - 1) & 1));  // MMAs of the previous use done
-          const float* src = vimg + (size_t)(b0 + c / 4) * kVimgBlockFloats + (size_t)(c & 3) * 8192;
-          const uint32_t mb = tc::smem_u32(full + st);
-          asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mb), "r"(32768) : "memory");
-          asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                           ring + st * 32768),
-                       "l"(src), "r"(32768), "r"(mb)
-                       : "memory");
+          const int bc = blk_ctr + blk;
+          const float* src = vimg + (size_t)(b0 + blk) * kVimgBlockFloats;
+#pragma unroll
+          for (int kc = 0; kc < 4; ++kc) {
+            if (bc > 0) tc::mbar_wait_parity(empty + kc, (uint32_t)((bc - 1) & 1));  // MMAs of the previous use done
+            const uint32_t mb = tc::smem_u32(full + kc);
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mb), "r"(32768) : "memory");
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                             ring + kc * 32768),
+                         "l"(src + kc * 8192), "r"(32768), "r"(mb)
+                         : "memory");
+          }
         }
-        if ((c & 3) == 0) prefetch_tile(b0 + c / 4 + 3);
+        prefetch_tile(b0 + blk + 3);
         __syncwarp();
       }
     } else if (warp == 4) {
       // ---------------- MMA issuer ----------------
-      if (lane == 0) {
-        for (int c = 0; c < nblk * 4; ++c) {
-          const int cc = chunk_ctr + c, st = cc % kU2Stages, use = cc / kU2Stages;
-          const int kc = c & 3, bc = blk_ctr + c / 4, buf = bc & 1, ub = bc >> 1;
-          if (kc == 0 && ub > 0) tc::mbar_wait_parity(acce + buf, (uint32_t)((ub - 1) & 1));  // accumulator drained
-          tc::mbar_wait_parity(full + st, (uint32_t)(use & 1));
-          asm volatile("tcgen05.fence::after_thread_sync;");
-          const uint32_t a_hi = ring + st * 2 * 16384, a_lo = a_hi + 16384;
-          const uint32_t b_hi = Bt + (2 * kc) * 8192, b_lo = Bt + (2 * kc + 1) * 8192;
+      // The whole warp runs the loop (uniform control flow, so descriptors stay in uniform registers -- with a
+      // lane-0 branch every MMA cost ~22 issue slots of ELECT/R2UR and the issue loop itself was the
+      // bottleneck); one elected lane issues.
+      for (int blk = 0; blk < nblk; ++blk) {
+        const int bc = blk_ctr + blk, buf = bc & 1, ub = bc >> 1;
+        if (ub > 0) tc::mbar_wait_parity(acce + buf, (uint32_t)((ub - 1) & 1));  // accumulator drained
+        const uint32_t acc = tmem + 64 * buf;
 #pragma unroll
-          for (int ks = 0; ks < 4; ++ks) {
-            const uint64_t dah = tc::umma_desc(a_hi + 32 * ks), dal = tc::umma_desc(a_lo + 32 * ks);
-            const uint64_t dbh = tc::umma_desc(b_hi + 32 * ks), dbl = tc::umma_desc(b_lo + 32 * ks);
-            tc::mma_tf32_n64(tmem + 64 * buf, dal, dbh, (kc > 0 || ks > 0) ? 1u : 0u);
-            tc::mma_tf32_n64(tmem + 64 * buf, dah, dbl, 1u);
-            tc::mma_tf32_n64(tmem + 64 * buf, dah, dbh, 1u);
+        for (int kc = 0; kc < 4; ++kc) {
+          tc::mbar_wait_parity(full + kc, (uint32_t)(bc & 1));
+          asm volatile("tcgen05.fence::after_thread_sync;");
+          if (tc::elect_one()) {
+            const uint64_t dah = tc::umma_desc(ring + kc * 32768), dal = tc::umma_desc(ring + kc * 32768 + 16384);
+            const uint64_t dbh = tc::umma_desc(Bt + (2 * kc) * 8192), dbl = tc::umma_desc(Bt + (2 * kc + 1) * 8192);
+#pragma unroll
+            for (int ks = 0; ks < 4; ++ks) {  // + 32 bytes of K per step = + 2 in the descriptor's address field
+              tc::mma_tf32_n64(acc, dal + 2 * ks, dbh + 2 * ks, (kc > 0 || ks > 0) ? 1u : 0u);
+              tc::mma_tf32_n64(acc, dah + 2 * ks, dbl + 2 * ks, 1u);
+              tc::mma_tf32_n64(acc, dah + 2 * ks, dbh + 2 * ks, 1u);
+            }
+            tc::umma_commit(empty + kc);               // stage free once these MMAs have read it
+            if (kc == 3) tc::umma_commit(accf + buf);  // accumulator complete
           }
-          tc::umma_commit(empty + st);               // stage free once these MMAs have read it
-          if (kc == 3) tc::umma_commit(accf + buf);  // accumulator complete
+          __syncwarp();
         }
       }
     } else if (warp < 4) {
@@ -1569,7 +1582,6 @@ __global__ void __launch_bounds__(kU2Threads, 1)
         finish(S1, rb, 1, x1);
       }
     }
-    chunk_ctr += nblk * 4;
     blk_ctr += nblk;
     __syncthreads();  // item done: every MMA that reads the Y tile has completed (epilogue saw the last accumulator)
   }
