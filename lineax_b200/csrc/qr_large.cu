@@ -1327,17 +1327,17 @@ __global__ void __launch_bounds__(kTcThreads, 2)
 //   qr_vsplit_kernel  splits V ONCE per outer block into the exact shared-memory operand images
 //                     (swizzled 128 x 32 tiles, hi then lo: 32 KB per K-chunk) in the workspace, and
 //   qr_update128_ws_kernel runs three jobs concurrently in one persistent CTA per SM:
-//     warp 5     PRODUCER: one thread copies a chunk's 32 KB image global -> shared with cp.async.bulk
-//                (mbarrier complete_tx) into a 4-stage ring; the other lanes prefetch A2 tiles into L2
-//     warp 4     one thread issues the 12 tcgen05.mma of a chunk as soon as its stage is full, commits the
-//                stage back to the producer and, after the 4th chunk, the accumulator to the epilogue
-//     warps 0-3  EPILOGUE: A2 tile loaded BEFORE the accumulator is waited for, TMEM -> registers, turned
-//                around in shared memory, subtracted and stored; two TMEM accumulators (2 x 64 columns)
-//                let the MMAs of row block b + 1 run under the epilogue of block b.
+//     warp 9     PRODUCER: one thread copies the 16 KB hi / lo images global -> shared with cp.async.bulk
+//                (mbarrier complete_tx) into a 4-slot ring; the other lanes prefetch A2 tiles into L2
+//     warp 8     one elected thread issues the tcgen05.mma (M128 N128 K8) of an image as soon as its slot is
+//                full, commits the slot back to the producer and, after the 8th image, the accumulator
+//     warps 0-7  EPILOGUE: A2 tile (128 x 128) loaded BEFORE the accumulator is waited for, TMEM -> registers,
+//                turned around in shared memory, subtracted and stored; two TMEM accumulators (2 x 128
+//                columns) let the MMAs of row block b + 1 run under the epilogue of block b.
 // All waits are mbarrier waits with a bounded spin that traps (no hang on a protocol error).
-constexpr int kU2Threads = 192;
-constexpr int kU2Stages = 4;  // == K-chunks per row block: chunk kc always uses stage kc
-constexpr size_t kU2Smem = 8 * 8192 + kU2Stages * 2 * 16384 + 8 * 4096 + 1024 + 128;
+constexpr int kU2Threads = 320;  // warps 0-7 epilogue, 8 MMA issuer, 9 producer
+constexpr int kU2Slots = 4;      // ring of 16 KB operand images
+constexpr size_t kU2Smem = 8 * 16384 + kU2Slots * 16384 + 8 * 4096 + 1024 + 128;
 constexpr size_t kVimgBlockFloats = 4 * 2 * 4096;  // one 128-row block: 4 K-chunks x {hi, lo} x 16 KB
 
 namespace tc {
@@ -1416,33 +1416,33 @@ __global__ void __launch_bounds__(kU2Threads, 1)
                            int j0, int ncols, int rblocks, int ntiles, int gsz) {
   extern __shared__ unsigned char smem_dyn[];
   const uint32_t sbase = (tc::smem_u32(smem_dyn) + 1023u) & ~1023u;  // shared-window addresses throughout
-  const uint32_t Bt = sbase;                                  // 4 K-chunks x {hi, lo} x (64 columns x 128 B)
-  const uint32_t ring = sbase + 8 * 8192;                     // kU2Stages x {hi 16 KB, lo 16 KB}
-  const uint32_t epi = ring + kU2Stages * 2 * 16384;          // 4 warps x 2 halves x 4 KB
+  const uint32_t Bt = sbase;                                  // 4 K-chunks x {hi, lo} x (128 columns x 128 B)
+  const uint32_t ring = sbase + 8 * 16384;                    // kU2Slots x 16 KB (one hi or lo image each)
+  const uint32_t epi = ring + kU2Slots * 16384;               // 8 warps x 4 KB
   unsigned char* gbase = smem_dyn + (sbase - tc::smem_u32(smem_dyn));
-  uint64_t* full = reinterpret_cast<uint64_t*>(gbase + 8 * 8192 + kU2Stages * 2 * 16384 + 8 * 4096);
-  uint64_t* empty = full + kU2Stages;
-  uint64_t* accf = empty + kU2Stages;
+  uint64_t* full = reinterpret_cast<uint64_t*>(gbase + 8 * 16384 + kU2Slots * 16384 + 8 * 4096);
+  uint64_t* empty = full + kU2Slots;
+  uint64_t* accf = empty + kU2Slots;
   uint64_t* acce = accf + 2;
   uint32_t* tslot = reinterpret_cast<uint32_t*>(acce + 2);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  // Work items = (group of `gsz` row blocks, tile), group-major and dealt round-robin: at any moment the
-  // CTAs are on the same few row groups, so the V images and A2 rows they share are found in L2.
+  // Work items = (group of `gsz` row blocks, 128-column tile), group-major and dealt round-robin: at any
+  // moment the CTAs are on the same few row groups, so the V images and A2 rows they share are found in L2.
   const int ngroups = (rblocks + gsz - 1) / gsz;
   const int nitems = ngroups * ntiles;
   if ((int)blockIdx.x >= nitems) return;  // uniform per CTA
   if (warp == 0) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tc::smem_u32(tslot)), "r"(128));
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tc::smem_u32(tslot)), "r"(256));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
   }
   if (tid == 0) {
-    for (int s2 = 0; s2 < kU2Stages; ++s2) {
+    for (int s2 = 0; s2 < kU2Slots; ++s2) {
       tc::mbar_init(full + s2, 1);
       tc::mbar_init(empty + s2, 1);
     }
     for (int q = 0; q < 2; ++q) {
       tc::mbar_init(accf + q, 1);
-      tc::mbar_init(acce + q, 128);
+      tc::mbar_init(acce + q, 256);
     }
     asm volatile("fence.mbarrier_init.release.cluster;");
   }
@@ -1450,26 +1450,28 @@ __global__ void __launch_bounds__(kU2Threads, 1)
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;");
   const uint32_t tmem = *tslot;
-  int blk_ctr = 0;    // row blocks this CTA has accumulated (same count in producer, issuer and epilogue)
+  int blk_ctr = 0;  // row blocks this CTA has accumulated (same count in producer, issuer and epilogue)
+  // A row block passes 8 images through the 4-slot ring, in the order lo(kc), hi(kc), kc = 0..3 (small
+  // terms first): image i = 2 kc + h uses slot i & 3, and it is that slot's use number 2 * blk_ctr + (i >> 2).
 
   for (int item = blockIdx.x; item < nitems; item += gridDim.x) {
     const int tile = item % ntiles, b0 = (item / ntiles) * gsz;
     const int b1 = min(rblocks, b0 + gsz);
     const int nblk = b1 - b0;
-    const int cbase = j0 + kOB + tile * 64;
-    const int cw = min(64, ncols - tile * 64);
+    const int cbase = j0 + kOB + tile * 128;
+    const int cw = min(128, ncols - tile * 128);
     // Y tile (all threads): tile row = column of A2 (N index), 128 B of K per chunk.  The previous
     // item's MMAs are complete (its epilogue waited for the last accumulator before the barrier below).
-    for (int idx = tid; idx < 2048; idx += kU2Threads) {
-      const int q = idx & 7, c = (idx >> 3) & 63, kc = idx >> 9;
-      const float4 y = c < cw ? tc::ldg128(Yt + (size_t)(tile * 64 + c) * kOB + 32 * kc + 4 * q)
+    for (int idx = tid; idx < 4096; idx += kU2Threads) {
+      const int q = idx & 7, c = (idx >> 3) & 127, kc = idx >> 10;
+      const float4 y = c < cw ? tc::ldg128(Yt + (size_t)(tile * 128 + c) * kOB + 32 * kc + 4 * q)
                               : make_float4(0.f, 0.f, 0.f, 0.f);
-      tc::split_sts(Bt + (2 * kc) * 8192, Bt + (2 * kc + 1) * 8192, c, q, y);
+      tc::split_sts(Bt + (2 * kc) * 16384, Bt + (2 * kc + 1) * 16384, c, q, y);
     }
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     __syncthreads();
 
-    if (warp == 5) {
+    if (warp == 9) {
       // ---------------- producer: bulk copies of the pre-split V images ----------------
       auto prefetch_tile = [&](int bb) {  // a later row block's A2 tile into L2 (the epilogue reads it)
         if (bb < b1) {
@@ -1478,73 +1480,81 @@ __global__ void __launch_bounds__(kU2Threads, 1)
             const int gr = j0 + bb * 128 + lane + 32 * i;
             if (gr < m) {
               const float* row = a + (size_t)gr * n + cbase;
-              asm volatile("prefetch.global.L2 [%0];" ::"l"(row));
-              if (cw > 32) asm volatile("prefetch.global.L2 [%0];" ::"l"(row + 32));
+#pragma unroll
+              for (int l = 0; l < 4; ++l)
+                if (cw > 32 * l) asm volatile("prefetch.global.L2 [%0];" ::"l"(row + 32 * l));
             }
           }
         }
       };
       prefetch_tile(b0 + 1);
       prefetch_tile(b0 + 2);
-      // 4 chunks per row block and a 4-stage ring: chunk kc always lands in stage kc, use = row-block count
       for (int blk = 0; blk < nblk; ++blk) {
         if (lane == 0) {
           const int bc = blk_ctr + blk;
           const float* src = vimg + (size_t)(b0 + blk) * kVimgBlockFloats;
 #pragma unroll
-          for (int kc = 0; kc < 4; ++kc) {
-            if (bc > 0) tc::mbar_wait_parity(empty + kc, (uint32_t)((bc - 1) & 1));  // MMAs of the previous use done
-            const uint32_t mb = tc::smem_u32(full + kc);
-            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mb), "r"(32768) : "memory");
+          for (int i = 0; i < 8; ++i) {
+            const int kc = i >> 1, h = (i & 1) ^ 1;  // lo image first
+            const int slot = i & 3, use = 2 * bc + (i >> 2);
+            if (use > 0) tc::mbar_wait_parity(empty + slot, (uint32_t)((use - 1) & 1));  // MMAs of the previous use done
+            const uint32_t mb = tc::smem_u32(full + slot);
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mb), "r"(16384) : "memory");
             asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                             ring + kc * 32768),
-                         "l"(src + kc * 8192), "r"(32768), "r"(mb)
+                             ring + slot * 16384),
+                         "l"(src + kc * 8192 + h * 4096), "r"(16384), "r"(mb)
                          : "memory");
           }
         }
         prefetch_tile(b0 + blk + 3);
         __syncwarp();
       }
-    } else if (warp == 4) {
+    } else if (warp == 8) {
       // ---------------- MMA issuer ----------------
       // The whole warp runs the loop (uniform control flow, so descriptors stay in uniform registers -- with a
-      // lane-0 branch every MMA cost ~22 issue slots of ELECT/R2UR and the issue loop itself was the
-      // bottleneck); one elected lane issues.
+      // lane-0 branch every MMA cost ~22 issue slots of ELECT/R2UR); one elected lane issues.  N = 128 per
+      // MMA: an M128 x N64 x K8 tf32 MMA reads 6 KB of operands from shared memory (48 cycles at 128 B/clk)
+      // for 34 cycles of math, N = 128 reads 8 KB for 68.
       for (int blk = 0; blk < nblk; ++blk) {
         const int bc = blk_ctr + blk, buf = bc & 1, ub = bc >> 1;
         if (ub > 0) tc::mbar_wait_parity(acce + buf, (uint32_t)((ub - 1) & 1));  // accumulator drained
-        const uint32_t acc = tmem + 64 * buf;
+        const uint32_t acc = tmem + 128 * buf;
 #pragma unroll
-        for (int kc = 0; kc < 4; ++kc) {
-          tc::mbar_wait_parity(full + kc, (uint32_t)(bc & 1));
+        for (int i = 0; i < 8; ++i) {
+          const int kc = i >> 1, slot = i & 3;
+          tc::mbar_wait_parity(full + slot, (uint32_t)((i >> 2) & 1));  // use 2 bc + (i >> 2)
           asm volatile("tcgen05.fence::after_thread_sync;");
           if (tc::elect_one()) {
-            const uint64_t dah = tc::umma_desc(ring + kc * 32768), dal = tc::umma_desc(ring + kc * 32768 + 16384);
-            const uint64_t dbh = tc::umma_desc(Bt + (2 * kc) * 8192), dbl = tc::umma_desc(Bt + (2 * kc + 1) * 8192);
+            const uint64_t da = tc::umma_desc(ring + slot * 16384);
+            const uint64_t dbh = tc::umma_desc(Bt + (2 * kc) * 16384), dbl = tc::umma_desc(Bt + (2 * kc + 1) * 16384);
 #pragma unroll
             for (int ks = 0; ks < 4; ++ks) {  // + 32 bytes of K per step = + 2 in the descriptor's address field
-              tc::mma_tf32_n64(acc, dal + 2 * ks, dbh + 2 * ks, (kc > 0 || ks > 0) ? 1u : 0u);
-              tc::mma_tf32_n64(acc, dah + 2 * ks, dbl + 2 * ks, 1u);
-              tc::mma_tf32_n64(acc, dah + 2 * ks, dbh + 2 * ks, 1u);
+              if ((i & 1) == 0) {
+                tc::mma_tf32(acc, da + 2 * ks, dbh + 2 * ks, (i > 0 || ks > 0) ? 1u : 0u);  // lo x hi
+              } else {
+                tc::mma_tf32(acc, da + 2 * ks, dbl + 2 * ks, 1u);  // hi x lo
+                tc::mma_tf32(acc, da + 2 * ks, dbh + 2 * ks, 1u);  // hi x hi
+              }
             }
-            tc::umma_commit(empty + kc);               // stage free once these MMAs have read it
-            if (kc == 3) tc::umma_commit(accf + buf);  // accumulator complete
+            tc::umma_commit(empty + slot);            // slot free once these MMAs have read it
+            if (i == 7) tc::umma_commit(accf + buf);  // accumulator complete
           }
           __syncwarp();
         }
       }
-    } else if (warp < 4) {
-      // ---------------- epilogue (warps 0-3 = TMEM lane quarters 0-3) ----------------
-      const uint32_t S0 = epi + warp * 8192, S1 = S0 + 4096;
+    } else if (warp < 8) {
+      // ------- epilogue: warp w owns TMEM lane quarter w & 3 (32 rows) and column half w >> 2 (64 columns) -------
+      const uint32_t S = epi + warp * 4096;
+      const int wq = warp & 3, ch = warp >> 2;
       const int c = lane & 7, lr = lane >> 3;
       auto load_x = [&](int rb, int qc, float4 (&x)[8]) {
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
-          const int gr = rb + 32 * warp + 4 * i + lr, col = 32 * qc + 4 * c;
+          const int gr = rb + 32 * wq + 4 * i + lr, col = 64 * ch + 32 * qc + 4 * c;
           if (gr < m && col < cw) x[i] = tc::ldg128(a + (size_t)gr * n + cbase + col);
         }
       };
-      auto to_smem = [&](uint32_t S, uint32_t taddr) {  // thread = row of the tile; written so reads are row-major
+      auto to_smem = [&](uint32_t taddr) {  // thread = row of the tile; written so reads are row-major
         uint32_t r[32];
         tc::tmem_ld32(taddr, r);
 #pragma unroll
@@ -1553,10 +1563,10 @@ __global__ void __launch_bounds__(kU2Threads, 1)
                      make_float4(__uint_as_float(r[4 * g4]), __uint_as_float(r[4 * g4 + 1]), __uint_as_float(r[4 * g4 + 2]),
                                  __uint_as_float(r[4 * g4 + 3])));
       };
-      auto finish = [&](uint32_t S, int rb, int qc, const float4 (&x)[8]) {
+      auto finish = [&](int rb, int qc, const float4 (&x)[8]) {
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
-          const int rr = 4 * i + lr, gr = rb + 32 * warp + rr, col = 32 * qc + 4 * c;
+          const int rr = 4 * i + lr, gr = rb + 32 * wq + rr, col = 64 * ch + 32 * qc + 4 * c;
           if (gr < m && col < cw) {
             const float4 p = tc::lds128(S + 16 * (rr * 8 + (c ^ (rr & 7))));
             float4 y = x[i];
@@ -1567,19 +1577,22 @@ __global__ void __launch_bounds__(kU2Threads, 1)
       };
       for (int blk = 0; blk < nblk; ++blk) {
         const int rb = j0 + (b0 + blk) * 128, bc = blk_ctr + blk, buf = bc & 1, ub = bc >> 1;
+        const uint32_t taddr = tmem + ((uint32_t)(32 * wq) << 16) + 128 * buf + 64 * ch;
         float4 x0[8], x1[8];
         load_x(rb, 0, x0);  // in flight while the accumulator is waited for
         load_x(rb, 1, x1);
         tc::mbar_wait_parity(accf + buf, (uint32_t)(ub & 1));
         asm volatile("tcgen05.fence::after_thread_sync;");
-        __syncwarp();  // the previous block's reads of S0/S1 are done
-        to_smem(S0, tmem + ((uint32_t)(32 * warp) << 16) + 64 * buf);
-        to_smem(S1, tmem + ((uint32_t)(32 * warp) << 16) + 64 * buf + 32);
+        __syncwarp();  // the previous block's reads of S are done
+        to_smem(taddr);
+        __syncwarp();
+        finish(rb, 0, x0);
+        __syncwarp();
+        to_smem(taddr + 32);
         asm volatile("tcgen05.fence::before_thread_sync;");
         tc::mbar_arrive(acce + buf);  // the MMAs of the block after next may overwrite this accumulator
         __syncwarp();
-        finish(S0, rb, 0, x0);
-        finish(S1, rb, 1, x1);
+        finish(rb, 1, x1);
       }
     }
     blk_ctr += nblk;
@@ -1587,7 +1600,7 @@ __global__ void __launch_bounds__(kU2Threads, 1)
   }
   asm volatile("tcgen05.fence::before_thread_sync;");
   __syncthreads();
-  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(128));
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(256));
 }
 
 // --------------------------------------------------- apply Q^T to one vector ----
@@ -1977,17 +1990,19 @@ int qr_large_factor(const T* A, T* a, T* taus, int m, int n, void* ws, size_t ws
       strips = (rblocks + per_strip - 1) / per_strip;
       static const bool up2 = [] { const char* e = getenv("LXB_QR_UP2"); return !(e && atoi(e) == 0); }();
       if (up2) {
-        // one persistent CTA per SM; groups of <= 32 row blocks, sized for about a whole number of rounds
-        const int64_t cells = (int64_t)ut * rblocks;
+        // one persistent CTA per SM; 128-column tiles, groups of <= 32 row blocks sized for about a whole
+        // number of rounds
+        const int ut2 = (ncols + 127) / 128;
+        const int64_t cells = (int64_t)ut2 * rblocks;
         const int rounds = (int)((cells + (int64_t)kNumSMs * 32 - 1) / ((int64_t)kNumSMs * 32));
         int gsz = (int)((cells + (int64_t)kNumSMs * rounds - 1) / ((int64_t)kNumSMs * rounds));
         gsz = gsz < 1 ? 1 : (gsz > rblocks ? rblocks : gsz);
-        const int64_t nitems = (int64_t)((rblocks + gsz - 1) / gsz) * ut;
+        const int64_t nitems = (int64_t)((rblocks + gsz - 1) / gsz) * ut2;
         const int g2 = (int)(nitems < kNumSMs ? nitems : kNumSMs);
         float* vimg = reinterpret_cast<float*>(w + pl.vimg_off);
         qr_vsplit_kernel<<<dim3(4, rblocks), 256, 0, st>>>(af, vimg, m, n, j0);
         LXB_CUDA_CHECK_LAUNCH();
-        qr_update128_ws_kernel<<<g2, kU2Threads, kU2Smem, st>>>(af, Yt, vimg, m, n, j0, ncols, rblocks, ut, gsz);
+        qr_update128_ws_kernel<<<g2, kU2Threads, kU2Smem, st>>>(af, Yt, vimg, m, n, j0, ncols, rblocks, ut2, gsz);
       } else {
         qr_update128_tc_kernel<<<dim3(ut, strips), kTcThreads, kUp128Smem, st>>>(af, Yt, m, n, j0, ncols, rblocks, per_strip);
       }
