@@ -1390,13 +1390,22 @@ __device__ __forceinline__ void split_sts(uint32_t hi, uint32_t lo, int r, int c
 }
 }  // namespace tc
 
-// V (columns j0 .. j0+127, rows j0 .., unit diagonal / zeros above applied) -> operand images.
+// V (columns j0 .. j0+127, rows j0 .., unit diagonal / zeros above applied) -> operand images:
+//   vimg   K-major SWIZZLE_128B tiles [128 rows][32 k] (A operand of the update, M = rows)
+//   vimgw  MN-major SWIZZLE_128B_BASE32B slabs [32 rows][128 k] (B operand of W = V^T A2, N = k, K = rows):
+//          the only shared-memory layout tcgen05 accepts for a transposed tf32 operand -- column blocks of
+//          32 k (4 KB apart = LBO), groups of 4 rows (512 B apart = SBO), 128 B rows whose 32-byte chunks are
+//          XORed with (row & 3).  tools/mn_major_probe.cu checks the layout against a host product.
 // grid (4 K-chunks, row blocks), 256 threads: thread = (row r0 + 32 i, 16-byte chunk q).
-__global__ void __launch_bounds__(256) qr_vsplit_kernel(const float* __restrict__ a, float* __restrict__ vimg, int m, int n,
-                                                        int j0) {
+__device__ __forceinline__ int mn32_off(int rs, int cb, int q) {  // row rs of a 32-row slab, column block cb, 16 B chunk q
+  return cb * 4096 + (rs >> 2) * 512 + (rs & 3) * 128 + ((((q >> 1) ^ (rs & 3)) << 5) | ((q & 1) << 4));
+}
+__global__ void __launch_bounds__(256) qr_vsplit_kernel(const float* __restrict__ a, float* __restrict__ vimg,
+                                                        float* __restrict__ vimgw, int m, int n, int j0) {
   const int kc = blockIdx.x, b = blockIdx.y, q = threadIdx.x & 7, r0 = threadIdx.x >> 3;
   unsigned char* hi = reinterpret_cast<unsigned char*>(vimg + (size_t)b * kVimgBlockFloats + (size_t)kc * 8192);
   unsigned char* lo = hi + 16384;
+  unsigned char* wimg = reinterpret_cast<unsigned char*>(vimgw + (size_t)b * kVimgBlockFloats);
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
     const int r = r0 + 32 * i, gr = j0 + b * 128 + r;
@@ -1407,8 +1416,219 @@ __global__ void __launch_bounds__(256) qr_vsplit_kernel(const float* __restrict_
       v.z = vmask<float>(v.z, gr, j0, 32 * kc + 4 * q + 2);
       v.w = vmask<float>(v.w, gr, j0, 32 * kc + 4 * q + 3);
     }
-    tc::split_store(hi, lo, r, q, v);
+    float4 h, l;
+    h.x = tc::tf32_rn(v.x); l.x = tc::tf32_rn(v.x - h.x);
+    h.y = tc::tf32_rn(v.y); l.y = tc::tf32_rn(v.y - h.y);
+    h.z = tc::tf32_rn(v.z); l.z = tc::tf32_rn(v.z - h.z);
+    h.w = tc::tf32_rn(v.w); l.w = tc::tf32_rn(v.w - h.w);
+    *reinterpret_cast<float4*>(hi + tc::sw128(r, q)) = h;
+    *reinterpret_cast<float4*>(lo + tc::sw128(r, q)) = l;
+    unsigned char* slab = wimg + (r >> 5) * 32768;  // slab = 32 rows: hi 16 KB, lo 16 KB
+    *reinterpret_cast<float4*>(slab + mn32_off(r & 31, kc, q)) = h;
+    *reinterpret_cast<float4*>(slab + 16384 + mn32_off(r & 31, kc, q)) = l;
   }
+}
+
+// W = V^T A2 (row-group partials), warp specialised like the update below and WITHOUT transposed staging:
+// both operands are fed MN-major (rows = K), so a slab of 32 rows x 128 columns of A2 is split hi/lo
+// where it lands (the transposing register shuffles of qr_wbig_tc_kernel were most of its instructions), and
+// the V operand is a bulk copy of the pre-split slab image.
+//   warps 0-3   DRAIN: every 4 slabs (48 MMAs -- longer TMEM sums pick up the accumulator's truncation bias)
+//               the finished accumulator is added to a 128 x 128 fp32 tile in shared memory
+//   warps 4-11  PRODUCERS: A2 slab global -> registers (two slabs in flight) -> hi/lo -> stage
+//   warp 12     one elected thread issues 12 tcgen05.mma (M128 N128 K8) per slab into one of two accumulators
+//   warp 13     bulk copies of the V slab images; other lanes prefetch A2 rows into L2
+// Wp[grp][k][c], grp = blockIdx.y = a range of `pb` row blocks; lane of TMEM = column c, TMEM column = k.
+constexpr int kW3Threads = 448;
+constexpr size_t kW3Smem = 65536 + 2 * 65536 + 1024 + 128;
+__device__ __forceinline__ uint64_t umma_desc_mn32(uint32_t saddr) {  // MN-major, SWIZZLE_128B_BASE32B, LBO 4096, SBO 512
+  return (uint64_t)((saddr >> 4) & 0x3fffu) | ((uint64_t)(4096 >> 4) << 16) | ((uint64_t)(512 >> 4) << 32) | ((uint64_t)1 << 46) |
+         ((uint64_t)1 << 61);
+}
+constexpr uint32_t kIdescMN = tc::kIdesc | (1u << 15) | (1u << 16);  // both operands transposed (MN-major)
+__device__ __forceinline__ void mma_tf32_mn(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(tmem_d),
+      "l"(da), "l"(db), "r"(kIdescMN), "r"(accumulate)
+      : "memory");
+}
+
+__global__ void __launch_bounds__(kW3Threads, 1)
+    qr_wbig_ws_kernel(const float* __restrict__ a, const float* __restrict__ vimgw, float* __restrict__ Wp, int m, int n, int j0,
+                      int cbase0, int ncols, int rblocks, int pb) {
+  extern __shared__ unsigned char smem_dyn[];
+  const uint32_t sbase = (tc::smem_u32(smem_dyn) + 1023u) & ~1023u;
+  const uint32_t accs = sbase;            // fp32 [128 k][128 c]
+  const uint32_t stg = sbase + 65536;     // 2 stages x {A hi, A lo, B hi, B lo} x 16 KB
+  unsigned char* gbase = smem_dyn + (sbase - tc::smem_u32(smem_dyn));
+  uint64_t* fullA = reinterpret_cast<uint64_t*>(gbase + 65536 + 2 * 65536);
+  uint64_t* fullB = fullA + 2;
+  uint64_t* empty = fullB + 2;
+  uint64_t* accf = empty + 2;
+  uint64_t* acce = accf + 2;
+  uint32_t* tslot = reinterpret_cast<uint32_t*>(acce + 2);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int tile = blockIdx.x, grp = blockIdx.y;
+  const int cbase = cbase0 + tile * 128;
+  const int cw = min(128, ncols - tile * 128);
+  const int b0 = grp * pb, b1 = min(rblocks, b0 + pb);
+  const int nslabs = (b1 - b0) * 4;  // > 0: the host launches ceil(rblocks / pb) groups
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tc::smem_u32(tslot)), "r"(256));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  if (tid == 0) {
+    for (int q = 0; q < 2; ++q) {
+      tc::mbar_init(fullA + q, 256);
+      tc::mbar_init(fullB + q, 1);
+      tc::mbar_init(empty + q, 1);
+      tc::mbar_init(accf + q, 1);
+      tc::mbar_init(acce + q, 128);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;");
+  }
+  for (int i = tid; i < 4096; i += kW3Threads) tc::sts128(accs + 16 * i, make_float4(0.f, 0.f, 0.f, 0.f));
+  asm volatile("tcgen05.fence::before_thread_sync;");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;");
+  const uint32_t tmem = *tslot;
+  // slab s: stage s & 1 (use s >> 1); accumulator group g = s >> 2 in TMEM buffer g & 1 (use g >> 1)
+
+  if (warp >= 4 && warp < 12) {
+    // ---------------- producers ----------------
+    const int pt = tid - 128;            // 0..255
+    const int c4 = pt & 31, rr = pt >> 5;  // float4 column c4 of rows rr + 8 i
+    const int cb = c4 >> 3, q = c4 & 7;
+    const bool cok = 4 * c4 < cw;
+    auto load_a = [&](int s, float4 (&v)[4]) {
+      const int rb = j0 + b0 * 128 + s * 32;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int gr = rb + rr + 8 * i;
+        v[i] = (s < nslabs && cok && gr < m) ? tc::ldg128(a + (size_t)gr * n + cbase + 4 * c4) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+    };
+    auto push = [&](int s, const float4 (&v)[4]) {
+      const int st = s & 1, use = s >> 1;
+      if (use > 0) tc::mbar_wait_parity(empty + st, (uint32_t)((use - 1) & 1));
+      const uint32_t Ahi = stg + st * 65536, Alo = Ahi + 16384;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int off = mn32_off(rr + 8 * i, cb, q);
+        float4 h, l;
+        h.x = tc::tf32_rn(v[i].x); l.x = tc::tf32_rn(v[i].x - h.x);
+        h.y = tc::tf32_rn(v[i].y); l.y = tc::tf32_rn(v[i].y - h.y);
+        h.z = tc::tf32_rn(v[i].z); l.z = tc::tf32_rn(v[i].z - h.z);
+        h.w = tc::tf32_rn(v[i].w); l.w = tc::tf32_rn(v[i].w - h.w);
+        tc::sts128(Ahi + off, h);
+        tc::sts128(Alo + off, l);
+      }
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      tc::mbar_arrive(fullA + st);
+    };
+    float4 va[4], vb[4];
+    load_a(0, va);
+    load_a(1, vb);
+    for (int s = 0; s < nslabs; s += 2) {  // nslabs is a multiple of 4
+      push(s, va);
+      load_a(s + 2, va);
+      push(s + 1, vb);
+      load_a(s + 3, vb);
+    }
+  } else if (warp == 13) {
+    // ---------------- V slab images (bulk copies) + L2 prefetch of A2 ----------------
+    auto prefetch_block = [&](int bb) {
+      if (bb < b1) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int gr = j0 + bb * 128 + lane + 32 * i;
+          if (gr < m) {
+            const float* row = a + (size_t)gr * n + cbase;
+#pragma unroll
+            for (int l = 0; l < 4; ++l)
+              if (cw > 32 * l) asm volatile("prefetch.global.L2 [%0];" ::"l"(row + 32 * l));
+          }
+        }
+      }
+    };
+    prefetch_block(b0 + 1);
+    prefetch_block(b0 + 2);
+    for (int s = 0; s < nslabs; ++s) {
+      if (lane == 0) {
+        const int st = s & 1, use = s >> 1;
+        if (use > 0) tc::mbar_wait_parity(empty + st, (uint32_t)((use - 1) & 1));
+        const float* src = vimgw + (size_t)(b0 + (s >> 2)) * kVimgBlockFloats + (size_t)(s & 3) * 8192;
+        const uint32_t mb = tc::smem_u32(fullB + st);
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mb), "r"(32768) : "memory");
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                         stg + st * 65536 + 32768),
+                     "l"(src), "r"(32768), "r"(mb)
+                     : "memory");
+      }
+      if ((s & 3) == 0) prefetch_block(b0 + (s >> 2) + 3);
+      __syncwarp();
+    }
+  } else if (warp == 12) {
+    // ---------------- MMA issuer (whole warp, one elected lane issues) ----------------
+    for (int s = 0; s < nslabs; ++s) {
+      const int st = s & 1, use = s >> 1, g = s >> 2, buf = g & 1, ub = g >> 1;
+      if ((s & 3) == 0 && ub > 0) tc::mbar_wait_parity(acce + buf, (uint32_t)((ub - 1) & 1));  // accumulator drained
+      tc::mbar_wait_parity(fullA + st, (uint32_t)(use & 1));
+      tc::mbar_wait_parity(fullB + st, (uint32_t)(use & 1));
+      asm volatile("tcgen05.fence::after_thread_sync;");
+      if (tc::elect_one()) {
+        const uint32_t sa = stg + st * 65536;
+        const uint64_t dah = umma_desc_mn32(sa), dal = umma_desc_mn32(sa + 16384);
+        const uint64_t dbh = umma_desc_mn32(sa + 32768), dbl = umma_desc_mn32(sa + 49152);
+        const uint32_t acc = tmem + 128 * buf;
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks) {  // 8 rows of K = 1 KB further on: + 64 in the address field
+          mma_tf32_mn(acc, dal + 64 * ks, dbh + 64 * ks, ((s & 3) != 0 || ks > 0) ? 1u : 0u);  // small terms first
+          mma_tf32_mn(acc, dah + 64 * ks, dbl + 64 * ks, 1u);
+          mma_tf32_mn(acc, dah + 64 * ks, dbh + 64 * ks, 1u);
+        }
+        tc::umma_commit(empty + st);
+        if ((s & 3) == 3) tc::umma_commit(accf + buf);
+      }
+      __syncwarp();
+    }
+  } else if (warp < 4) {
+    // ---------------- drain: TMEM accumulator -> += shared-memory tile ----------------
+    const int ngrp = nslabs >> 2;
+    for (int g = 0; g < ngrp; ++g) {
+      const int buf = g & 1, ub = g >> 1;
+      tc::mbar_wait_parity(accf + buf, (uint32_t)(ub & 1));
+      asm volatile("tcgen05.fence::after_thread_sync;");
+#pragma unroll
+      for (int qc = 0; qc < 4; ++qc) {
+        uint32_t r[32];
+        tc::tmem_ld32(tmem + ((uint32_t)(32 * warp) << 16) + 128 * buf + 32 * qc, r);
+#pragma unroll
+        for (int k = 0; k < 32; ++k) {
+          const uint32_t ad = accs + 4 * ((32 * qc + k) * 128 + tid);
+          float t;
+          asm volatile("ld.shared.f32 %0, [%1];" : "=f"(t) : "r"(ad) : "memory");
+          t += __uint_as_float(r[k]);
+          asm volatile("st.shared.f32 [%0], %1;" ::"r"(ad), "f"(t) : "memory");
+        }
+      }
+      asm volatile("tcgen05.fence::before_thread_sync;");
+      tc::mbar_arrive(acce + buf);
+    }
+    if (tid < cw) {
+      float* out = Wp + ((size_t)grp * kOB) * ncols + tile * 128 + tid;
+#pragma unroll 8
+      for (int k = 0; k < kOB; ++k) {
+        float t;
+        asm volatile("ld.shared.f32 %0, [%1];" : "=f"(t) : "r"(accs + 4 * (k * 128 + tid)) : "memory");
+        out[(size_t)k * ncols] = t;
+      }
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;");
+  __syncthreads();
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(256));
 }
 
 __global__ void __launch_bounds__(kU2Threads, 1)
@@ -1799,7 +2019,7 @@ __global__ void __launch_bounds__(1024) qr_rsolve_kernel(const T* __restrict__ a
 template <typename T>
 struct QrLargePlan {
   int nb, nb_panel, rows_cta;
-  size_t smem_panel, ws_bytes, wp_off, w2_off, t_off, gpart_off, gfull_off, y_off, tbig_off, yt_off, vimg_off;
+  size_t smem_panel, ws_bytes, wp_off, w2_off, t_off, gpart_off, gfull_off, y_off, tbig_off, yt_off, vimg_off, vimgw_off;
   int ngroups, in_smem;
   bool ok;
 };
@@ -1831,6 +2051,8 @@ QrLargePlan<T> qr_large_plan(int m, int n) {
   pl.yt_off = off; off += (size_t)kOB * pad4(n);      // Y = T^T W, transposed
   off = (off + 255) & ~(size_t)255;
   pl.vimg_off = off;                                  // pre-split operand images of an outer block's V
+  if (sizeof(T) == 4 && n > kOB) off += (size_t)((m + 127) / 128) * kVimgBlockFloats;
+  pl.vimgw_off = off;                                 // the same V as MN-major slab images (W = V^T A2)
   if (sizeof(T) == 4 && n > kOB) off += (size_t)((m + 127) / 128) * kVimgBlockFloats;
   pl.ws_bytes = off * sizeof(T);
   pl.ok = true;
@@ -1947,6 +2169,7 @@ int qr_large_factor(const T* A, T* a, T* taus, int m, int n, void* ws, size_t ws
     LXB_CUDA_TRY(cudaFuncSetAttribute(qr_wbig_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kWbigSmem));
     LXB_CUDA_TRY(cudaFuncSetAttribute(qr_update128_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kUp128Smem));
     LXB_CUDA_TRY(cudaFuncSetAttribute(qr_update128_ws_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kU2Smem));
+    LXB_CUDA_TRY(cudaFuncSetAttribute(qr_wbig_ws_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kW3Smem));
     const size_t tb_smem = (size_t)2 * kOB * (kOB + 1) * sizeof(float);
     LXB_CUDA_TRY(cudaFuncSetAttribute(qr_tbig_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tb_smem));
     const size_t wp_cap = (size_t)pl.ngroups * kPB * pad4(n);  // elements reserved for row-group partials
@@ -1972,18 +2195,35 @@ int qr_large_factor(const T* A, T* a, T* taus, int m, int n, void* ws, size_t ws
       LXB_CUDA_CHECK_LAUNCH();
       qr_tbig_kernel<<<1, kTbigThreads, tb_smem, st>>>(Yt, reinterpret_cast<const float*>(taus) + j0, Tb, 1);
       LXB_CUDA_CHECK_LAUNCH();
-      // W = V^T A2 (row-group partials), Y = T^T W, A2 -= V Y
+      // V operand images (both kernels below), W = V^T A2 (row-group partials), Y = T^T W, A2 -= V Y
+      const int rblocks = (m - j0 + 127) / 128;
+      float* vimg = reinterpret_cast<float*>(w + pl.vimg_off);
+      float* vimgw = reinterpret_cast<float*>(w + pl.vimgw_off);
+      qr_vsplit_kernel<<<dim3(4, rblocks), 256, 0, st>>>(af, vimg, vimgw, m, n, j0);
+      LXB_CUDA_CHECK_LAUNCH();
       const int wt = (ncols + 127) / 128;
-      int ng = (6 * kNumSMs + wt - 1) / wt;
+      static const bool w3 = [] { const char* e = getenv("LXB_QR_W3"); return !(e && atoi(e) == 0); }();
       const int cap = (int)(wp_cap / ((size_t)kOB * ncols));
-      ng = ng > cap ? cap : ng;
-      ng = ng > kW2MaxGroups ? kW2MaxGroups : (ng < 1 ? 1 : ng);
-      qr_wbig_tc_kernel<false><<<dim3(wt, ng), kTcThreads, kWbigSmem, st>>>(af, Wpf, m, n, j0, jend, ncols, ng);
+      int ng;
+      if (w3) {
+        // one CTA per SM, about two waves; a group is a whole number of 128-row blocks
+        ng = (2 * kNumSMs) / wt;
+        ng = ng > cap ? cap : ng;
+        ng = ng > kW2MaxGroups ? kW2MaxGroups : (ng < 1 ? 1 : ng);
+        ng = ng > rblocks ? rblocks : ng;
+        const int pb = (rblocks + ng - 1) / ng;
+        ng = (rblocks + pb - 1) / pb;
+        qr_wbig_ws_kernel<<<dim3(wt, ng), kW3Threads, kW3Smem, st>>>(af, vimgw, Wpf, m, n, j0, jend, ncols, rblocks, pb);
+      } else {
+        ng = (6 * kNumSMs + wt - 1) / wt;
+        ng = ng > cap ? cap : ng;
+        ng = ng > kW2MaxGroups ? kW2MaxGroups : (ng < 1 ? 1 : ng);
+        qr_wbig_tc_kernel<false><<<dim3(wt, ng), kTcThreads, kWbigSmem, st>>>(af, Wpf, m, n, j0, jend, ncols, ng);
+      }
       LXB_CUDA_CHECK_LAUNCH();
       qr_wfinish128_kernel<<<(ncols + kWf128Cols - 1) / kWf128Cols, 256, 0, st>>>(Wpf, Tb, Yt, ncols, ng);
       LXB_CUDA_CHECK_LAUNCH();
       const int ut = (ncols + 63) / 64;
-      const int rblocks = (m - j0 + 127) / 128;
       int strips = (4 * 2 * kNumSMs + ut - 1) / ut;
       strips = strips < 1 ? 1 : (strips > rblocks ? rblocks : strips);
       const int per_strip = (rblocks + strips - 1) / strips;
@@ -1999,9 +2239,6 @@ int qr_large_factor(const T* A, T* a, T* taus, int m, int n, void* ws, size_t ws
         gsz = gsz < 1 ? 1 : (gsz > rblocks ? rblocks : gsz);
         const int64_t nitems = (int64_t)((rblocks + gsz - 1) / gsz) * ut2;
         const int g2 = (int)(nitems < kNumSMs ? nitems : kNumSMs);
-        float* vimg = reinterpret_cast<float*>(w + pl.vimg_off);
-        qr_vsplit_kernel<<<dim3(4, rblocks), 256, 0, st>>>(af, vimg, m, n, j0);
-        LXB_CUDA_CHECK_LAUNCH();
         qr_update128_ws_kernel<<<g2, kU2Threads, kU2Smem, st>>>(af, Yt, vimg, m, n, j0, ncols, rblocks, ut2, gsz);
       } else {
         qr_update128_tc_kernel<<<dim3(ut, strips), kTcThreads, kUp128Smem, st>>>(af, Yt, m, n, j0, ncols, rblocks, per_strip);
