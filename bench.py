@@ -670,7 +670,7 @@ def bench_large(ctx, args, workload, with_cpu):
             def solve(A_=A, b_=b):
                 aq, taus = _ops.qr_factor(A_)
                 return _ops.qr_solve(aq, taus, b_, False), z, z + 1
-            kernel = "qr_panel + qr_wpartial + qr_update (blocked Householder, tcgen05 3xTF32 trailing update)"
+            kernel = "qr_panel + qr_wbig_ws + qr_update128_ws (two-level blocked Householder, warp-specialised tcgen05 3xTF32 W and trailing update)"
         n_mv = lambda k: 0
         rows_local = hi - lo
 
