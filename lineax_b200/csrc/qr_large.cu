@@ -449,6 +449,7 @@ __global__ void __launch_bounds__(kW2Threads, sizeof(T) == 4 ? 4 : 2)
 // W2[k][c] = sum_k' T[k'][k] * (sum_g Wp[g][k'][c]); 32 columns x 8 slices of 4 k per CTA.  The
 // group sum is latency bound (a few loads per thread), so 8 groups x 4 k are loaded before any add.
 constexpr int kWfCols = 32;
+constexpr int kWqSlices = 8;
 template <typename T>
 __global__ void __launch_bounds__(256)
     qr_wfinish_kernel(const T* __restrict__ Wp, const T* __restrict__ Tm, T* __restrict__ W2, int ncols,
@@ -484,6 +485,28 @@ __global__ void __launch_bounds__(256)
     for (int kp = 0; kp <= k; ++kp) s = fma_(Ts[kp * kPB + k], wsum[kp][cl], s);  // T upper triangular
     W2[(size_t)k * ncols + c] = s;
   }
+}
+
+// Pre-reduction of the row-group partials for the narrow inner updates of the two-level blocking: those use up
+// to 592 row groups (one wave of the W kernel at 4 CTAs per SM) but only <= 96 columns, so qr_wfinish_kernel
+// ran 3 CTAs that each walked all the groups serially (75 us per launch, latency bound).  Here
+// `nslices` x (32 * ncols / 256) CTAs each sum a contiguous slice of the groups in a fixed order;
+// qr_wfinish_kernel then sums the nslices results.  Wq[s][e] = sum_{g in slice s} Wp[g][e], e < 32 * ncols.
+template <typename T>
+__global__ void __launch_bounds__(256)
+    qr_wpresum_kernel(const T* __restrict__ Wp, T* __restrict__ Wq, int elems, int ngroups, int per_slice) {
+  const int e = blockIdx.x * 256 + threadIdx.x, sl = blockIdx.y;
+  if (e >= elems) return;
+  const int g_lo = sl * per_slice, g_hi = min(ngroups, g_lo + per_slice);
+  T s = T(0);
+  for (int g0 = g_lo; g0 < g_hi; g0 += 8) {
+    T t[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) t[u] = g0 + u < g_hi ? Wp[(size_t)(g0 + u) * elems + e] : T(0);
+#pragma unroll
+    for (int u = 0; u < 8; ++u) s += t[u];
+  }
+  Wq[(size_t)sl * elems + e] = s;
 }
 
 // ------------------------------------------------------------------ K4: update ----
@@ -2019,7 +2042,7 @@ __global__ void __launch_bounds__(1024) qr_rsolve_kernel(const T* __restrict__ a
 template <typename T>
 struct QrLargePlan {
   int nb, nb_panel, rows_cta;
-  size_t smem_panel, ws_bytes, wp_off, w2_off, t_off, gpart_off, gfull_off, y_off, tbig_off, yt_off, vimg_off, vimgw_off;
+  size_t smem_panel, ws_bytes, wp_off, w2_off, t_off, gpart_off, gfull_off, y_off, tbig_off, yt_off, vimg_off, vimgw_off, wq_off;
   int ngroups, in_smem;
   bool ok;
 };
@@ -2047,6 +2070,7 @@ QrLargePlan<T> qr_large_plan(int m, int n) {
   pl.wp_off = off; off += (size_t)pl.ngroups * kPB * pad4(n);
   pl.w2_off = off; off += (size_t)kPB * pad4(n);
   pl.y_off = off; off += pad4(m);
+  pl.wq_off = off; off += (size_t)kWqSlices * kPB * pad4(n);  // pre-reduced row-group partials (narrow updates)
   pl.tbig_off = off; off += (size_t)kOB * kOB;        // T of an outer block (two-level blocking)
   pl.yt_off = off; off += (size_t)kOB * pad4(n);      // Y = T^T W, transposed
   off = (off + 255) & ~(size_t)255;
@@ -2105,7 +2129,15 @@ int qr_large_factor(const T* A, T* a, T* taus, int m, int n, void* ws, size_t ws
       qr_wpartial_kernel<T><<<dim3(wtiles, ngroups), kW2Threads, w_smem, st>>>(a, Wp, m, n, j0, ncols, ngroups);
     }
     LXB_CUDA_CHECK_LAUNCH();
-    qr_wfinish_kernel<T><<<(ncols + kWfCols - 1) / kWfCols, 256, 0, st>>>(Wp, Tm, W2, ncols, ngroups);
+    if (ngroups > 64) {
+      T* Wq = w + pl.wq_off;
+      const int elems = kPB * ncols, per_slice = (ngroups + kWqSlices - 1) / kWqSlices;
+      qr_wpresum_kernel<T><<<dim3((elems + 255) / 256, kWqSlices), 256, 0, st>>>(Wp, Wq, elems, ngroups, per_slice);
+      LXB_CUDA_CHECK_LAUNCH();
+      qr_wfinish_kernel<T><<<(ncols + kWfCols - 1) / kWfCols, 256, 0, st>>>(Wq, Tm, W2, ncols, kWqSlices);
+    } else {
+      qr_wfinish_kernel<T><<<(ncols + kWfCols - 1) / kWfCols, 256, 0, st>>>(Wp, Tm, W2, ncols, ngroups);
+    }
     LXB_CUDA_CHECK_LAUNCH();
     constexpr int V = 16 / (int)sizeof(T);
     // tensor-core update is the default for fp32; LXB_QR_TC=0 selects the plain fp32 FMA kernel
