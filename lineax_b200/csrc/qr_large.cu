@@ -2267,8 +2267,11 @@ int qr_large_factor(const T* A, T* a, T* taus, int m, int n, void* ws, size_t ws
         const int ut2 = (ncols + 127) / 128;
         const int64_t cells = (int64_t)ut2 * rblocks;
         const int rounds = (int)((cells + (int64_t)kNumSMs * 32 - 1) / ((int64_t)kNumSMs * 32));
-        int gsz = (int)((cells + (int64_t)kNumSMs * rounds - 1) / ((int64_t)kNumSMs * rounds));
-        gsz = gsz < 1 ? 1 : (gsz > rblocks ? rblocks : gsz);
+        // row groups per tile so that groups x tiles fits `rounds` full rounds of the CTAs (rounding the group
+        // SIZE instead could spill a few items into one more round: 310 items on 148 CTAs at m = 32 768)
+        int gpt = (int)(((int64_t)kNumSMs * rounds) / ut2);
+        gpt = gpt < 1 ? 1 : (gpt > rblocks ? rblocks : gpt);
+        const int gsz = (rblocks + gpt - 1) / gpt;
         const int64_t nitems = (int64_t)((rblocks + gsz - 1) / gsz) * ut2;
         const int g2 = (int)(nitems < kNumSMs ? nitems : kNumSMs);
         qr_update128_ws_kernel<<<g2, kU2Threads, kU2Smem, st>>>(af, Yt, vimg, m, n, j0, ncols, rblocks, ut2, gsz);
