@@ -10,8 +10,16 @@
 //     K3 qr_wfinish_kernel : W2 = T^T (sum_g Wp[g])
 //     K4 qr_update_kernel  : A2 -= V W2                        (register-tiled 64x128 tiles)
 // The 1e-5 parity budget rules out plain TF32 tensor-core tiles (SURVEY.md section 7 "hard parts"):
-// the fp32 update runs on tcgen05 with the 3xTF32 split (qr_update_tc_kernel), everything else is
-// fp32/fp64 SIMT FMA.
+// the fp32 updates run on tcgen05 with the 3xTF32 split (qr_update_tc_kernel for the 32-wide ones).
+// fp32, aligned, n > 128 uses TWO-LEVEL blocking: four panels per 128-column outer block (K2-K4 only
+// on the <= 96 columns inside the block, partials pre-reduced by qr_wpresum_kernel), then once per
+// outer block, K = 128 on the tensor cores:
+//     qr_wbig_tc_kernel<true> + qr_gsum + qr_tbig : T (128 x 128) from the Gram matrix of V
+//     qr_vsplit_kernel      : V -> pre-split hi/lo operand images (K-major and MN-major)
+//     qr_wbig_ws_kernel     : Wp[g] = V^T A2, warp specialised, MN-major operands
+//     qr_wfinish128_kernel  : Y = T^T sum_g Wp[g]
+//     qr_update128_ws_kernel: A2 -= V Y, warp specialised, bulk-copied V images
+// Everything else is fp32/fp64 SIMT FMA.
 #include "krylov_grid.cuh"
 #include "krylov_grid_api.cuh"
 
@@ -920,8 +928,10 @@ __global__ void __launch_bounds__(kTcThreads)
 
 // Transposed staging for the W = V^T A2 product on tcgen05 (qr_wbig_tc_kernel below): the contraction runs
 // over the ROWS, so the 32-row chunks are TRANSPOSED while they are staged and both operands become K-major,
-// the configuration of the update kernels (an MN-major encoding of the untransposed chunks returned zeros:
-// tools/tc_mn_major_probe.cu).  Thread (rq = tid & 7, cq) loads a 4 x 4 block (rows 4rq.., columns 4cq..),
+// the configuration of the update kernels.  (An MN-major encoding of the untransposed chunks in the plain
+// SWIZZLE_128B layout returns zeros; tf32 needs SWIZZLE_128B_BASE32B -- tools/mn_major_probe.cu -- which
+// is what qr_wbig_ws_kernel, the default for the trailing W, uses.  This kernel remains for the Gram
+// matrix of V and as the LXB_QR_W3=0 fallback.)  Thread (rq = tid & 7, cq) loads a 4 x 4 block (rows 4rq.., columns 4cq..),
 // transposes it in registers and stores four 16-byte K-chunks; a quarter warp covers the 8 chunks of one
 // tile row, so the stores are conflict free.  (A K = 32 version of this kernel, one panel at a time, was
 // validated in situ this round and measured no faster than the SIMT W kernel -- 317 vs 313 ms -- and removed.)
