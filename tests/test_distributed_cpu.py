@@ -247,6 +247,76 @@ def test_row_sharded_gmres_decomposition_world2_gloo(tmp_path):
     assert np.array_equal(x0, x1)
 
 
+def _cg_rows_worker(rank, world, port, out_dir):
+    """The decomposition cg_dist.cu uses, restated with numpy + gloo: rank p owns a block of rows of the SPD operator and
+    the same slice of every vector; per iteration an all-gather of the search direction, an all-reduce of <Ap, p>, and ONE
+    round carrying <r, r> with the two max-norms of the convergence test (cg.py:114-227, stabilise_every = 10)."""
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    import oracle
+    from oracle import gen
+    from lineax_b200._shard import shard_bounds
+
+    n, tol, stabilise_every = 157, 1e-10, 10
+    a, b, _ = gen.easy_problem(7, n, np.float64, spd=True)
+    bounds = shard_bounds(n, world)
+    lo, hi = bounds[rank], bounds[rank + 1]
+    al, bl = a[lo:hi], b[lo:hi]
+    rcond = 2 * np.finfo(np.float64).eps * n
+
+    def allsum(x):
+        t = torch.as_tensor(np.array([x], dtype=np.float64))
+        dist.all_reduce(t)
+        return float(t.item())
+
+    def allmax2(x, y):
+        t = torch.as_tensor(np.array([x, y], dtype=np.float64))
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t[0]), float(t[1])
+
+    def gather(vl):
+        width = max(bounds[r + 1] - bounds[r] for r in range(world))
+        mine = torch.zeros(width, dtype=torch.float64)
+        mine[: hi - lo] = torch.as_tensor(np.ascontiguousarray(vl))
+        parts = [torch.empty(width, dtype=torch.float64) for _ in range(world)]
+        dist.all_gather(parts, mine)
+        return torch.cat([parts[r][: bounds[r + 1] - bounds[r]] for r in range(world)]).numpy()
+
+    with np.errstate(all="ignore"):
+        yl = np.zeros(hi - lo)
+        rl = bl - al @ gather(yl)
+        pl = rl.copy()
+        gamma = allsum(pl @ rl)
+        norm1 = norm2 = np.inf
+        step, ms = 0, 10 * n
+        while gamma > 0 and step < ms and (norm1 > 1 or norm2 > 1):
+            ql = al @ gather(pl)
+            ip = allsum(ql @ pl)
+            alpha = gamma / ip if abs(ip) > 100 * rcond * abs(gamma) else np.nan
+            step += 1
+            dl = alpha * pl
+            yl = yl + dl
+            rl = bl - al @ gather(yl) if step % stabilise_every == 0 else rl - alpha * ql
+            gn = allsum(rl @ rl)
+            norm1, norm2 = allmax2(np.max(np.abs(rl / (tol + tol * np.abs(bl)))), np.max(np.abs(dl / (tol + tol * np.abs(yl)))))
+            beta, gamma = gn / gamma, gn
+            pl = rl + beta * pl
+    x = gather(yl)
+    xr, rr, st = oracle.cg(a, b, tol, tol)
+    assert rr == 0 and abs(step - st["num_steps"]) <= 1, (step, st["num_steps"], rr)
+    assert np.abs(x - xr).max() <= 1e-9 * np.abs(xr).max()
+    np.save(os.path.join(out_dir, f"cg{rank}.npy"), x)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_row_sharded_cg_decomposition_world2_gloo(tmp_path):
+    world = 2
+    mp.spawn(_cg_rows_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    x0, x1 = np.load(tmp_path / "cg0.npy"), np.load(tmp_path / "cg1.npy")
+    assert np.array_equal(x0, x1)
+
+
 def _tsqr_worker(rank, world, port, out_dir):
     """RowShardedQR (TSQR) and its `lx.linear_solve(RowShardedMatrixLinearOperator, b_local, lx.QR())` entry on
     a world-2 gloo group with the oracle-backed CPU doubles: local QR, all-gather of the R factors, small QR."""
